@@ -1,0 +1,239 @@
+#!/usr/bin/env python
+"""Benchmark of the STARCOP hot path on B200 (contract: see the task statement / DESIGN.md).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 3 --warmup 1      # reference CPU path (oracle port)
+
+Metric (BASELINE.json): 512x512 hyperspectral tiles/s for one HyperSTARCOP train step
+(forward + weighted BCE + backward + Adam, BatchNorm in training mode).  Workload at every N:
+BASELINE.json configs[1] per GPU -- U-Net fwd/bwd on synthetic 512x512x(mag1c+RGB) tiles, bs=16,
+bf16 storage / fp32 accumulate (weak scaling: per-GPU work fixed, gradients all-reduced over NCCL).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UNET_TRAIN_GFLOP_PER_TILE = 80.24      # fprop + dgrad + wgrad, C=4, 512x512
+UNET_FWD_GFLOP_PER_TILE = 26.798
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=16, help="tiles per GPU (configs[1]: 16)")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [s.strip() for s in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:          # noqa: BLE001
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def cpu_reference_step_rate(size, steps, warmup, tiles=2):
+    """Reference CPU path (oracle port of the reference's PyTorch fp32 module, all host threads):
+    fwd + loss + bwd + Adam on a bounded sample of `tiles` tiles per step."""
+    from oracle.module import get_model as oracle_get_model
+    from starcop_b200 import synthetic
+    from starcop_b200.settings import default_settings
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    m = oracle_get_model(default_settings(pos_weight=1.0))
+    opt = m.configure_optimizers()["optimizer"]
+    batch = synthetic.hyperstarcop_batch(tiles, size=size, seed=0)
+    m.train()
+    ts = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = m.training_step(batch, i)
+        loss.backward()
+        opt.step()
+        if i >= warmup:
+            ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return tiles / med, med, torch.get_num_threads(), f"{tiles} tiles of {size}x{size}x4 per step, {steps} timed steps, median"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    rate, med, cores, sample = cpu_reference_step_rate(args.size, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": "512x512 hyperspectral tiles/sec (train step)", "value": rate,
+            "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"HyperSTARCOP U-Net train step, {args.size}x{args.size}x4 tiles (CPU PyTorch fp32)"},
+            "cpu_baseline": {"value": rate, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from starcop_b200 import _lib, synthetic
+    from starcop_b200.model_setup import get_model
+    from starcop_b200.settings import default_settings
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    torch.manual_seed(0)                       # same initial weights on every rank (DDP broadcast equivalent)
+    model = get_model(default_settings(pos_weight=1.0, compute_dtype=args.dtype), None).to(dev)
+    model.train()
+    B, S = args.batch, args.size
+    host = synthetic.hyperstarcop_batch(B, size=S, seed=100 + rank)        # rank-seeded tiles
+    pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
+    resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
+
+    def grad_sync(flat):
+        if world > 1:
+            dist.all_reduce(flat)              # NCCL sum over NVLink; the mean is folded into Adam's grad_scale
+            return 1.0 / world
+        return 1.0
+
+    def step_resident():
+        return model.train_step_fused(resident, grad_sync=grad_sync)
+
+    staging = {k: torch.empty_like(v, device=dev) for k, v in host.items() if torch.is_tensor(v)}
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        for k, v in pinned.items():
+            if torch.is_tensor(v):
+                staging[k].copy_(v, non_blocking=True)
+        loss = model.train_step_fused(staging, grad_sync=grad_sync)
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        return loss
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = _lib.launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _lib.launch_count() - c0
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_resident, args.steps, max(args.warmup, 3))
+    ms_e2e, _ = timed(step_e2e, args.steps, 1)
+    sampler.stop_flag = True
+
+    tiles = world * B * args.steps
+    value = tiles / (ms / 1e3)
+    e2e_val = tiles / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+
+    roof = model.network.bench_dominant_kernel(B, S) if hasattr(model.network, "bench_dominant_kernel") else None
+    pk, pk_kind = peaks()
+    if roof is not None:
+        roof["peak"] = pk["bf16_tflops"]
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["peak_source"] = f"{pk_kind} burst bf16 (kernel timed alone)"
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            rate, med, cores, sample = cpu_reference_step_rate(S, 3, 1)
+            cpu = {"value": rate, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample}
+        line = {
+            "metric": "512x512 hyperspectral tiles/sec (train step)", "value": value, "unit": "tiles/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"configs[1]: HyperSTARCOP U-Net fwd+bwd+Adam, {S}x{S}x(mag1c+RGB) tiles, bs={B}/GPU, "
+                                   f"{args.dtype} storage fp32 accumulate, BN train mode",
+                       "global_batch": world * B, "tile": [S, S, 4], "parallelism": f"dp{world}",
+                       "l2": "per-step working set (activations > 2 GB) exceeds the 126 MB L2"},
+            "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "unet_tflops": value * UNET_TRAIN_GFLOP_PER_TILE / 1e3,
+            "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

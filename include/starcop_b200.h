@@ -1,0 +1,175 @@
+/* starcop_b200 C ABI -- the drop-in boundary of the B200-native STARCOP hot path.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all memory
+ *     (PyTorch allocates it); the library never allocates persistent device memory;
+ *   - every entry point launches on the `stream` it is given (a cudaStream_t passed as void*),
+ *     never synchronises the device, never throws; it returns SC_OK (0) or a negative sc_status;
+ *   - activation tensors are NHWC with an explicit channel stride `ld` (elements), so a channel
+ *     slice of a wider buffer (the decoder's concat buffers) is addressed without a copy;
+ *   - `dtype` is SC_F32 or SC_BF16 and names the STORAGE type of activations; all arithmetic
+ *     accumulates in fp32 (statistics and loss sums in fp64);
+ *   - there is no CPU fallback anywhere behind this header.
+ *
+ * Each entry point cites the reference call it replaces (paths relative to the STARCOP tree).
+ */
+#ifndef STARCOP_B200_H
+#define STARCOP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SC_OK = 0,
+  SC_ERR_BAD_ARG = -1,      /* shape / alignment / dtype contract violated */
+  SC_ERR_CUDA = -2,         /* a CUDA runtime call failed (see sc_last_cuda_error) */
+  SC_ERR_UNSUPPORTED = -3,  /* configuration not implemented by this kernel */
+  SC_ERR_NO_DEVICE = -4     /* no sm_100 device / driver entry point unavailable */
+} sc_status;
+
+enum { SC_F32 = 0, SC_BF16 = 1 };
+enum { SC_ACT_NONE = 0, SC_ACT_RELU = 1, SC_ACT_RELU6 = 2 };
+
+int sc_abi_version(void);
+/* last cudaError_t seen by the library on this thread, as text (host pointer, static storage) */
+const char* sc_last_cuda_error(void);
+
+/* ---- A1: DataNormalizer.normalize_x (starcop/data/normalizer_module.py:134-135) -------------
+ * x: (B,C,H,W) f32 NCHW raw products.  off/fac/lo/hi: C doubles each (device).  f64_path is a bit
+ * mask of which reference parameter arrays are float64 (bit0 offsets, bit1 factors): the reference
+ * builds them with np.array(python numbers), so one non-integer entry promotes the whole
+ * subtraction / division to float64 before the final .float().
+ * out_nhwc: (B,H,W,ld_out) `dtype`, channels [C,ld_out) zero filled; may be NULL.
+ * out_nchw: (B,C,H,W) f32 normalised copy ("input_norm", model_module.py:196); may be NULL. */
+int sc_normalize_pack(const float* x, const double* off, const double* fac, const double* lo,
+                      const double* hi, int f64_path, int B, int C, int H, int W,
+                      void* out_nhwc, int ld_out, int dtype, float* out_nchw, void* stream);
+
+/* ---- A2: smp.Unet(mobilenet_v2) building blocks (model_module.py:98, 238-251) ---------------
+ * Dense convolution, NHWC, weights packed [KH*KW][Cin][Cout] f32 (sc_pack_weights).
+ * y[n,ho,wo,co] (+)= sum x[n, ho*stride-pad+kh, wo*stride-pad+kw, ci] * w[kh,kw,ci,co] (+ bias)
+ * accumulate != 0 adds onto the existing y (gradient accumulation for residual / skip fan-out). */
+int sc_conv_fprop(const void* x, int ldx, const float* w_packed, const float* bias, void* y, int ldy,
+                  int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                  int dtype, int accumulate, void* stream);
+/* dW[co,ci,kh,kw] (OIHW f32, torch layout) += sum_p x[p*stride-pad+k][ci] * dy[p][co]; caller zeroes dW */
+int sc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw,
+                  int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                  int dtype, void* stream);
+/* OIHW f32 -> packed [KH*KW][Cin][Cout] f32; flip_transpose != 0 builds the data-gradient filter
+ * (taps mirrored, Cin/Cout swapped) so that dgrad of a stride-1 conv is sc_conv_fprop on dy. */
+int sc_pack_weights(const float* w_oihw, float* w_packed, int Cout, int Cin, int KH, int KW,
+                    int flip_transpose, void* stream);
+
+/* depthwise 3x3, pad 1, stride 1|2; weights (C,1,3,3) f32 torch layout.
+ * The *_bnact variants read x through the producer's BatchNorm+activation on the fly:
+ * xin = act(x*scale[c]+shift[c]) (scale==NULL -> identity), so the x6 expanded tensor of an
+ * inverted-residual block is never written normalised. */
+int sc_dwconv_fprop(const void* x, int ldx, const float* scale, const float* shift, int act,
+                    const float* w, void* y, int ldy, int N, int H, int W, int C, int stride,
+                    int dtype, void* stream);
+int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* dx, int lddx,
+                    int N, int H, int W, int C, int stride, int dtype, void* stream);
+int sc_dwconv_wgrad(const void* x, int ldx, const float* scale, const float* shift, int act,
+                    const void* dy, int lddy, float* dw, int N, int H, int W, int C, int stride,
+                    int dtype, void* stream);
+
+/* training-mode BatchNorm2d (eps 1e-5, momentum 0.1 -- torchvision / smp defaults), split as
+ * statistics -> finalize -> apply so that the normalise+activation runs in the consumer.
+ * stats: sums[0..C) += sum_p y, sums[C..2C) += sum_p y*y   (fp64; caller zeroes) */
+int sc_bn_stats(const void* y, int ldy, double* sums, int64_t P, int C, int dtype, void* stream);
+/* training != 0: mean/var from sums over P pixels, running stats updated (unbiased var);
+ * training == 0: uses running_mean/var.  Emits scale = gamma*invstd, shift = beta - mean*scale,
+ * and saves mean / invstd for the backward. */
+int sc_bn_finalize(const double* sums, int64_t P, int C, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, float momentum, float eps, int training,
+                   float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+/* z = act(y*scale+shift) (+ residual); written at channel stride ldz; upsample2 != 0 writes each
+ * pixel to its 2x2 nearest-neighbour block of a (N,2H,2W,ldz) buffer (F.interpolate(scale 2,
+ * "nearest") + torch.cat of the decoder fused into the producer's store). */
+int sc_bn_act(const void* y, int ldy, const float* scale, const float* shift, int act,
+              const void* residual, int ldr, void* z, int ldz, int N, int H, int W, int C,
+              int upsample2, int dtype, void* stream);
+/* BN backward, phase 1: with g = dz * act'(y*scale+shift) (dz optionally 2x2 sum-pooled from a
+ * (N,2H,2W,lddz) buffer when pooled != 0), red[0..C) += sum g, red[C..2C) += sum g*xhat (fp64). */
+int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void* y, int ldy,
+                     const float* scale, const float* shift, const float* mean, const float* invstd,
+                     int act, double* red, int N, int H, int W, int C, int dtype, void* stream);
+/* phase 2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dgamma += red[C..], dbeta += red[..C) */
+int sc_bn_bwd_apply(const void* dz, int lddz, int pooled, const void* y, int ldy,
+                    const float* scale, const float* shift, const float* mean, const float* invstd,
+                    const float* gamma, int act, const double* red, void* dy, int lddy,
+                    float* dgamma, float* dbeta, int N, int H, int W, int C, int dtype, void* stream);
+/* out (+)= a  [2x2 sum-pooled when pooled]; plain gradient routing for skip / residual fan-out */
+int sc_add_into(const void* a, int lda, int pooled, void* out, int ldo, int accumulate,
+                int N, int H, int W, int C, int dtype, void* stream);
+
+/* segmentation head Conv2d(16->1, k3, pad1, bias) (smp SegmentationHead) -- bandwidth bound, no MMA */
+int sc_head_fprop(const void* x, int ldx, const float* w, const float* bias, float* logits,
+                  int N, int H, int W, int C, int dtype, void* stream);
+int sc_head_bwd(const void* x, int ldx, const float* w, const float* dlogits, void* dx, int lddx,
+                float* dw, float* dbias, int N, int H, int W, int C, int dtype, void* stream);
+
+/* ---- A3/A4/A6: weighted BCE + decisions + confusion counts in ONE pass ----------------------
+ * (model_module.py:76-79 train, :115-135 val, :191-212 batch_with_preds; torchmetrics
+ * ConfusionMatrix.update).  logits/y/w: n = B*HW f32 (w may be NULL = no weight_loss).
+ * loss_sum[0] += sum l*w (fp64).  Optional outputs (NULL to skip):
+ *   grad        d mean(l*w)/d logits * grad_scale            (ATen's backward form)
+ *   cm          int64[4] += [[TN,FP],[FN,TP]] for pred = logits >= 0      (val_step, :124)
+ *   pred_count  int64[B] += per-tile sum of that pred                     (pred_classification)
+ *   cm_sig / pred_count_sig: the same for pred = sigmoid(logits) > .5     (batch_with_preds :204)
+ *   prediction, loss_px, loss_px_w (f32), pred_binary, differences (int64) per pixel. */
+int sc_bce_fused(const float* logits, const float* y, const float* w, float pos_weight,
+                 int B, int64_t HW, float grad_scale, double* loss_sum, float* grad,
+                 int64_t* cm, int64_t* pred_count, int64_t* cm_sig, int64_t* pred_count_sig,
+                 float* prediction, float* loss_px, float* loss_px_w, int64_t* pred_binary,
+                 int64_t* differences, void* stream);
+
+/* ---- A16: torch.optim.Adam(lr) on one flat fp32 arena (model_module.py:172-174) -------------
+ * step_host is the 1-based step count; grad_scale multiplies g first (DDP mean). */
+int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                 float beta2, float eps, int step_host, float grad_scale, void* stream);
+
+/* ---- A8/A10: mag1c matched filter (starcop/models/mag1c.py:176-348) -------------------------
+ * x: (G, P, ldx) BIP radiance rows, S window bands starting at x (caller offsets the pointer to
+ * the first window band); template: S elements of `fp64 ? double : float`.
+ * valid: optional (G,P) uint8 mask (func_by_groups, mag1c.py:161-172): groups with <= 10 valid
+ * pixels are skipped and every non-valid pixel is written as -9999.
+ * mf_out / albedo_out: (G,P) same float type.  workspace from sc_mag1c_workspace_bytes. */
+int64_t sc_mag1c_workspace_bytes(int G, int P, int S, int fp64);
+int sc_mag1c_filter(const void* x, int64_t ldx, const void* tmpl, const uint8_t* valid,
+                    void* mf_out, void* albedo_out, int G, int P, int S, int num_iter, double alpha,
+                    int fp64, void* workspace, void* stream);
+
+/* ---- A11/A13: band ratio product (starcop/data/feature_extration.py:32-56) ------------------
+ * per tile: exact 5/95 percentiles (np.percentile linear) of each band by radix select, inlier
+ * sums, c = sum_bg/sum_sig, R = (c*sig-bg)/(bg+1e-6), R = zero_value where both < 1e-6. */
+int64_t sc_ratio_workspace_bytes(int T, int64_t HW);
+int sc_ratio_product(const float* bg, const float* sig, float* out, int T, int64_t HW,
+                     float percentile, float zero_value, void* workspace, void* stream);
+int sc_weight_mag1c(const float* mag1c, float* out, int64_t n, void* stream);
+
+/* ---- A14: binary opening with the 3x3 cross (starcop/baselines.py:25-27, 54-58) ------------- */
+int sc_threshold_opening(const float* pred, float threshold, int64_t* out, uint8_t* scratch,
+                         int B, int H, int W, void* stream);
+
+/* ---- tcgen05 tensor-core path (bf16 storage, fp32 accumulate in TMEM) -----------------------
+ * Implicit-GEMM convolution: A = activation tile fetched by TMA (shifted box per filter tap, zero
+ * fill = padding), B = packed bf16 weights [Cout][KH*KW][Cin], accumulators in TMEM.
+ * Supported: stride 1, KH=KW in {1,3}, Cin % 16 == 0, Cout % 16 == 0, W % 16 == 0 or H*W % 128 == 0.
+ * Optional epilogue: per-channel sum / sum-of-squares of the stored outputs into `stats` (fp64). */
+int sc_tc_supported(void);
+int sc_tc_pack_weights(const float* w_oihw, void* w_bf16, int Cout, int Cin, int KH, int KW,
+                       int flip_transpose, int cin_pad, int cout_pad, void* stream);
+int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void* y, int ldy, double* stats,
+                     int N, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
+int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw,
+                     int N, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STARCOP_B200_H */

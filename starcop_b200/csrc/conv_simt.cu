@@ -1,0 +1,507 @@
+// fp32-FMA implicit-GEMM convolutions (NHWC).  This is the exact-fp32 path: it carries the parity
+// claim against the reference's fp32 PyTorch network and serves every layer the tcgen05 path does
+// not (stem Cin=4 stride 2, channel counts that are not multiples of 16).  Depthwise 3x3 kernels
+// (bandwidth bound) live here too.
+#include "common.cuh"
+
+using namespace sc;
+
+// ------------------------------------------------------------------------------------------------
+// dense conv fprop: M = output pixels, N = Cout, K = KH*KW*Cin (tap-major, channel-minor)
+// 256 threads, block tile BM x BN, thread tile TM x TN, BK = 16, register-prefetch double buffer.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int BM, int BN, int TM, int TN, bool VEC>
+__global__ void __launch_bounds__(256)
+conv_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ wp, const float* __restrict__ bias,
+                  T* __restrict__ y, int ldy, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                  int stride, int pad, int Ho, int Wo, int accumulate) {
+  constexpr int BK = 16;
+  constexpr int TX = BN / TN;            // threads along N
+  static_assert((BM / TM) * TX == 256, "tile/thread mismatch");
+  constexpr int A_PER_T = BM * BK / 256; // elements of A per thread (8 for BM=128, 16 for BM=256)
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int64_t M = (int64_t)N * Ho * Wo;
+  const int K = KH * KW * Cin;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  // A loader: thread owns pixel row a_m and A_PER_T consecutive k starting at a_k
+  constexpr int KGROUPS = BK / 8;                 // 2 groups of 8 k per pixel
+  constexpr int ROWS_PER_PASS = 256 / KGROUPS;    // 128 pixel rows per pass
+  constexpr int PASSES = BM / ROWS_PER_PASS;      // 1 (BM=128) or 2 (BM=256)
+  static_assert(A_PER_T == 8 * PASSES, "A loader geometry");
+  const int a_r = tid % ROWS_PER_PASS;       // consecutive threads -> consecutive pixels: conflict-free As stores
+  const int a_kg = tid / ROWS_PER_PASS;
+  int a_n[PASSES], a_h[PASSES], a_w[PASSES];
+  bool a_ok[PASSES];
+#pragma unroll
+  for (int ps = 0; ps < PASSES; ++ps) {
+    int64_t m = m0 + a_r + ps * ROWS_PER_PASS;
+    a_ok[ps] = m < M;
+    int64_t mm = a_ok[ps] ? m : 0;
+    a_w[ps] = (int)(mm % Wo);
+    int64_t t = mm / Wo;
+    a_h[ps] = (int)(t % Ho);
+    a_n[ps] = (int)(t / Ho);
+  }
+  // B loader: BK x BN floats, 4 per thread
+  constexpr int B_VECS = BK * BN / 4;
+  float areg[PASSES][8];
+  float4 breg[(B_VECS + 255) / 256];
+
+  auto load_tiles = [&](int k0) {
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps) {
+      int kb = k0 + a_kg * 8;
+      if (VEC) {
+        // Cin % 8 == 0: the 8 k of this group share one tap
+        bool ok = a_ok[ps] && kb < K;
+        int tap = ok ? kb / Cin : 0, ci = ok ? kb - tap * Cin : 0;
+        int kh = tap / KW, kw = tap - kh * KW;
+        int ih = a_h[ps] * stride - pad + kh, iw = a_w[ps] * stride - pad + kw;
+        ok = ok && ih >= 0 && ih < H && iw >= 0 && iw < W;
+        if (ok) {
+          f8 v = load8<T>(x + (((int64_t)a_n[ps] * H + ih) * W + iw) * ldx + ci);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) areg[ps][i] = v.v[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) areg[ps][i] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          int k = kb + i;
+          float v = 0.f;
+          if (a_ok[ps] && k < K) {
+            int tap = k / Cin, ci = k - tap * Cin;
+            int kh = tap / KW, kw = tap - kh * KW;
+            int ih = a_h[ps] * stride - pad + kh, iw = a_w[ps] * stride - pad + kw;
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+              v = to_f<T>(x[(((int64_t)a_n[ps] * H + ih) * W + iw) * ldx + ci]);
+          }
+          areg[ps][i] = v;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < (B_VECS + 255) / 256; ++j) {
+      int v = tid + j * 256;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < B_VECS) {
+        int kk = v / (BN / 4), nn = (v % (BN / 4)) * 4;
+        int k = k0 + kk, n = n0 + nn;
+        if (k < K) {
+          const float* src = wp + (int64_t)k * Cout + n;
+          if (n + 3 < Cout && (Cout % 4 == 0)) {
+            r = *reinterpret_cast<const float4*>(src);
+          } else {
+            if (n < Cout) r.x = src[0];
+            if (n + 1 < Cout) r.y = src[1];
+            if (n + 2 < Cout) r.z = src[2];
+            if (n + 3 < Cout) r.w = src[3];
+          }
+        }
+      }
+      breg[j] = r;
+    }
+  };
+  auto store_tiles = [&]() {
+#pragma unroll
+    for (int ps = 0; ps < PASSES; ++ps)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) As[a_kg * 8 + i][a_r + ps * ROWS_PER_PASS] = areg[ps][i];
+#pragma unroll
+    for (int j = 0; j < (B_VECS + 255) / 256; ++j) {
+      int v = tid + j * 256;
+      if (v < B_VECS) {
+        int kk = v / (BN / 4), nn = (v % (BN / 4)) * 4;
+        *reinterpret_cast<float4*>(&Bs[kk][nn]) = breg[j];
+      }
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  load_tiles(0);
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    store_tiles();
+    __syncthreads();
+    if (k0 + BK < K) load_tiles(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int i = 0; i < TM; i += 4) {
+        float4 v = *reinterpret_cast<const float4*>(&As[kk][ty * TM + i]);
+        a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
+      }
+#pragma unroll
+      for (int j = 0; j < TN; j += 4) {
+        float4 v = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN + j]);
+        b[j] = v.x; b[j + 1] = v.y; b[j + 2] = v.z; b[j + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int64_t m = m0 + ty * TM + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int n = n0 + tx * TN + j;
+      if (n >= Cout) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      T* o = y + m * ldy + n;
+      if (accumulate) v += to_f<T>(*o);
+      *o = from_f<T>(v);
+    }
+  }
+}
+
+template <typename T, int BM, int BN, int TM, int TN>
+static int launch_fprop(const void* x, int ldx, const float* wp, const float* bias, void* y, int ldy, int N,
+                        int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int accumulate,
+                        cudaStream_t st) {
+  int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  int64_t M = (int64_t)N * Ho * Wo;
+  dim3 grid(ceil_div(M, BM), ceil_div(Cout, BN));
+  bool vec = (Cin % 8 == 0) && (ldx % 8 == 0);
+  if (vec)
+    conv_fprop_kernel<T, BM, BN, TM, TN, true><<<grid, 256, 0, st>>>((const T*)x, ldx, wp, bias, (T*)y, ldy, N, H, W,
+                                                                       Cin, Cout, KH, KW, stride, pad, Ho, Wo, accumulate);
+  else
+    conv_fprop_kernel<T, BM, BN, TM, TN, false><<<grid, 256, 0, st>>>((const T*)x, ldx, wp, bias, (T*)y, ldy, N, H, W,
+                                                                        Cin, Cout, KH, KW, stride, pad, Ho, Wo, accumulate);
+  return check_launch();
+}
+
+extern "C" int sc_conv_fprop(const void* x, int ldx, const float* w_packed, const float* bias, void* y, int ldy,
+                             int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dtype,
+                             int accumulate, void* stream) {
+  if (!x || !w_packed || !y || N <= 0 || Cin <= 0 || Cout <= 0 || stride < 1) return SC_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  SC_DISPATCH_DTYPE(dtype, {
+    if (Cout > 32)
+      return launch_fprop<T, 128, 64, 8, 4>(x, ldx, w_packed, bias, y, ldy, N, H, W, Cin, Cout, KH, KW, stride, pad, accumulate, st);
+    if (Cout > 16)
+      return launch_fprop<T, 128, 32, 4, 4>(x, ldx, w_packed, bias, y, ldy, N, H, W, Cin, Cout, KH, KW, stride, pad, accumulate, st);
+    return launch_fprop<T, 256, 16, 4, 4>(x, ldx, w_packed, bias, y, ldy, N, H, W, Cin, Cout, KH, KW, stride, pad, accumulate, st);
+  });
+  return SC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense conv wgrad: per tap, dW[ci][co] = sum_p x[p@tap][ci] * dy[p][co]; 64x64 tile, split over
+// pixels, fp32 atomics into the torch-layout (OIHW) gradient.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_wgrad_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int lddy, float* __restrict__ dw,
+                  int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo,
+                  int ci_tiles, int psplit) {
+  constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+  __shared__ float As[BK][BM + 4];   // [pixel][ci]
+  __shared__ float Bs[BK][BN + 4];   // [pixel][co]
+  const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+  const int ci0 = (blockIdx.x % ci_tiles) * BM;
+  const int tap = blockIdx.x / ci_tiles;
+  const int co0 = blockIdx.y * BN;
+  const int kh = tap / KW, kw = tap - kh * KW;
+  const int64_t P = (int64_t)N * Ho * Wo;
+  const int64_t chunk = ((P + psplit - 1) / psplit + BK - 1) / BK * BK;
+  const int64_t p_begin = (int64_t)blockIdx.z * chunk;
+  int64_t p_end = p_begin + chunk;
+  if (p_end > P) p_end = P;
+
+  // loader: 16 pixels x 64 channels = 1024 elements, 4 per thread: thread -> (pixel lr, 4 channels lc)
+  const int lr = tid / 16, lc = (tid % 16) * 4;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int64_t p0 = p_begin; p0 < p_end; p0 += BK) {
+    int64_t p = p0 + lr;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p < p_end) {
+      int wo = (int)(p % Wo);
+      int64_t t = p / Wo;
+      int ho = (int)(t % Ho);
+      int n = (int)(t / Ho);
+      int ih = ho * stride - pad + kh, iw = wo * stride - pad + kw;
+      if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+        const T* xp = x + (((int64_t)n * H + ih) * W + iw) * ldx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ci0 + lc + i < Cin) a[i] = to_f<T>(xp[ci0 + lc + i]);
+      }
+      const T* dp = dy + p * lddy;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (co0 + lc + i < Cout) b[i] = to_f<T>(dp[co0 + lc + i]);
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&As[lr][lc]) = make_float4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<float4*>(&Bs[lr][lc]) = make_float4(b[0], b[1], b[2], b[3]);
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
+      float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * TN]);
+      float aa[4] = {av.x, av.y, av.z, av.w}, bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+    }
+  }
+  const int KK = KH * KW;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int ci = ci0 + ty * TM + i;
+    if (ci >= Cin) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int co = co0 + tx * TN + j;
+      if (co >= Cout) continue;
+      atomicAdd(&dw[((int64_t)co * Cin + ci) * KK + tap], acc[i][j]);
+    }
+  }
+}
+
+extern "C" int sc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, int N, int H, int W,
+                             int Cin, int Cout, int KH, int KW, int stride, int pad, int dtype, void* stream) {
+  if (!x || !dy || !dw_oihw || N <= 0) return SC_ERR_BAD_ARG;
+  int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  int64_t P = (int64_t)N * Ho * Wo;
+  int ci_tiles = ceil_div(Cin, 64), co_tiles = ceil_div(Cout, 64);
+  int base = ci_tiles * KH * KW * co_tiles;
+  int psplit = (kNumSMs * 4 + base - 1) / base;
+  int64_t max_split = (P + 255) / 256;
+  if (psplit > max_split) psplit = (int)max_split;
+  if (psplit < 1) psplit = 1;
+  dim3 grid(ci_tiles * KH * KW, co_tiles, psplit);
+  SC_DISPATCH_DTYPE(dtype, (conv_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)x, ldx, (const T*)dy, lddy, dw_oihw, N, H, W, Cin, Cout, KH, KW, stride,
+                               pad, Ho, Wo, ci_tiles, psplit)));
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3 (pad 1, stride 1|2), optional BN+act of the producer applied on load
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ f8 load_bnact(const T* p, const f8& sc_, const f8& sh, bool has_bn, int act) {
+  f8 v = load8<T>(p);
+  if (has_bn) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v.v[i] = apply_act(fmaf(v.v[i], sc_.v[i], sh.v[i]), act);
+  }
+  return v;
+}
+
+template <typename T>
+__global__ void dwconv_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int act, const float* __restrict__ w,
+                                    T* __restrict__ y, int ldy, int N, int H, int W, int C, int stride, int Ho,
+                                    int Wo) {
+  int CV = C / 8;
+  int64_t total = (int64_t)N * Ho * Wo * CV;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    int64_t p = idx / CV;
+    int wo = (int)(p % Wo);
+    int64_t t = p / Wo;
+    int ho = (int)(t % Ho);
+    int n = (int)(t / Ho);
+    f8 sc_, sh;
+    bool has_bn = scale != nullptr;
+    if (has_bn) {
+      sc_ = load8<float>(scale + cv * 8);
+      sh = load8<float>(shift + cv * 8);
+    }
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      int ih = ho * stride - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int iw = wo * stride - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        f8 v = load_bnact<T>(x + (((int64_t)n * H + ih) * W + iw) * ldx + cv * 8, sc_, sh, has_bn, act);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v.v[i], w[(cv * 8 + i) * 9 + kh * 3 + kw], acc[i]);
+      }
+    }
+    f8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = acc[i];
+    store8<T>(y + p * ldy + cv * 8, o);
+  }
+}
+
+static int ew_blocks2(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+extern "C" int sc_dwconv_fprop(const void* x, int ldx, const float* scale, const float* shift, int act,
+                               const float* w, void* y, int ldy, int N, int H, int W, int C, int stride, int dtype,
+                               void* stream) {
+  if (!x || !w || !y || C % 8 || ldx % 8 || ldy % 8 || (stride != 1 && stride != 2)) return SC_ERR_BAD_ARG;
+  int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  SC_DISPATCH_DTYPE(dtype, (dwconv_fprop_kernel<T><<<ew_blocks2(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)x, ldx, scale, shift, act, w, (T*)y, ldy, N, H, W, C, stride, Ho, Wo)));
+  return check_launch();
+}
+
+// dx[n,ih,iw,c] = sum_{kh,kw : (ih+1-kh) % s == 0 ...} dy[n,(ih+1-kh)/s,(iw+1-kw)/s,c] * w[c,kh,kw]
+template <typename T>
+__global__ void dwconv_dgrad_kernel(const T* __restrict__ dy, int lddy, const float* __restrict__ w,
+                                    T* __restrict__ dx, int lddx, int N, int H, int W, int C, int stride, int Ho,
+                                    int Wo) {
+  int CV = C / 8;
+  int64_t total = (int64_t)N * H * W * CV;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    int64_t p = idx / CV;
+    int iw = (int)(p % W);
+    int64_t t = p / W;
+    int ih = (int)(t % H);
+    int n = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      int th = ih + 1 - kh;
+      if (th < 0 || th % stride) continue;
+      int ho = th / stride;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int tw = iw + 1 - kw;
+        if (tw < 0 || tw % stride) continue;
+        int wo = tw / stride;
+        if (wo >= Wo) continue;
+        f8 g = load8<T>(dy + (((int64_t)n * Ho + ho) * Wo + wo) * lddy + cv * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(g.v[i], w[(cv * 8 + i) * 9 + kh * 3 + kw], acc[i]);
+      }
+    }
+    f8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o.v[i] = acc[i];
+    store8<T>(dx + p * lddx + cv * 8, o);
+  }
+}
+
+extern "C" int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* dx, int lddx, int N, int H, int W,
+                               int C, int stride, int dtype, void* stream) {
+  if (!dy || !w || !dx || C % 8 || lddy % 8 || lddx % 8 || (stride != 1 && stride != 2)) return SC_ERR_BAD_ARG;
+  int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  int64_t total = (int64_t)N * H * W * (C / 8);
+  SC_DISPATCH_DTYPE(dtype, (dwconv_dgrad_kernel<T><<<ew_blocks2(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C, stride, Ho, Wo)));
+  return check_launch();
+}
+
+template <typename T>
+__global__ void dwconv_wgrad_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, int act, const T* __restrict__ dy, int lddy,
+                                    float* __restrict__ dw, int N, int H, int W, int C, int stride, int Ho, int Wo,
+                                    int CVB, int PL) {
+  extern __shared__ float smf[];   // [CVB*8][9]
+  int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
+  int cv = blockIdx.y * CVB + cvl;
+  for (int i = threadIdx.x; i < CVB * 72; i += blockDim.x) smf[i] = 0.f;
+  __syncthreads();
+  if (pl < PL && cv * 8 < C) {
+    f8 sc_, sh;
+    bool has_bn = scale != nullptr;
+    if (has_bn) {
+      sc_ = load8<float>(scale + cv * 8);
+      sh = load8<float>(shift + cv * 8);
+    }
+    float acc[9][8];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[tp][i] = 0.f;
+    int64_t P = (int64_t)N * Ho * Wo;
+    for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
+      int wo = (int)(p % Wo);
+      int64_t t = p / Wo;
+      int ho = (int)(t % Ho);
+      int n = (int)(t / Ho);
+      f8 g = load8<T>(dy + p * lddy + cv * 8);
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        int ih = ho * stride - 1 + kh;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          int iw = wo * stride - 1 + kw;
+          if (iw < 0 || iw >= W) continue;
+          f8 v = load_bnact<T>(x + (((int64_t)n * H + ih) * W + iw) * ldx + cv * 8, sc_, sh, has_bn, act);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[kh * 3 + kw][i] = fmaf(v.v[i], g.v[i], acc[kh * 3 + kw][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&smf[(cvl * 8 + i) * 9 + tp], acc[tp][i]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CVB * 72; i += blockDim.x) {
+    int c = blockIdx.y * CVB * 8 + i / 9;
+    if (c < C) atomicAdd(&dw[c * 9 + i % 9], smf[i]);
+  }
+}
+
+extern "C" int sc_dwconv_wgrad(const void* x, int ldx, const float* scale, const float* shift, int act,
+                               const void* dy, int lddy, float* dw, int N, int H, int W, int C, int stride,
+                               int dtype, void* stream) {
+  if (!x || !dy || !dw || C % 8 || ldx % 8 || lddy % 8 || (stride != 1 && stride != 2)) return SC_ERR_BAD_ARG;
+  int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  int CV = C / 8;
+  int CVB = CV < 64 ? CV : 64;      // 64*72 floats = 18 KB smem
+  int PL = 256 / CVB;
+  int gy = (CV + CVB - 1) / CVB;
+  int64_t P = (int64_t)N * Ho * Wo;
+  int64_t want = (P + PL * 8 - 1) / (PL * 8);
+  int64_t cap = (kNumSMs * 8) / gy;
+  if (cap < 1) cap = 1;
+  int bx = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+  dim3 grid(bx, gy);
+  size_t smem = (size_t)CVB * 72 * sizeof(float);
+  SC_DISPATCH_DTYPE(dtype, (dwconv_wgrad_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+                               (const T*)x, ldx, scale, shift, act, (const T*)dy, lddy, dw, N, H, W, C, stride, Ho,
+                               Wo, CVB, PL)));
+  return check_launch();
+}

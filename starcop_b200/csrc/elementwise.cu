@@ -1,0 +1,741 @@
+// Bandwidth-bound kernels of the STARCOP hot path: input normalisation, training-mode BatchNorm
+// (statistics / finalize / apply / backward), gradient routing, segmentation head, fused weighted
+// BCE + decisions + confusion counts, Adam.  All NHWC, 8-channel vectors, fp32 math, fp64 sums.
+#include "common.cuh"
+
+namespace sc {
+thread_local cudaError_t g_last_error = cudaSuccess;
+}
+using namespace sc;
+
+extern "C" int sc_abi_version(void) { return 1; }
+extern "C" const char* sc_last_cuda_error(void) { return cudaGetErrorString(sc::g_last_error); }
+
+// ------------------------------------------------------------------------------------------------
+// A1 normalize_x: clamp((x-off)/fac, lo, hi).float()  (normalizer_module.py:134-135)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void normalize_pack_kernel(const float* __restrict__ x, const double* __restrict__ off,
+                                      const double* __restrict__ fac, const double* __restrict__ lo,
+                                      const double* __restrict__ hi, int f64_path, int C, int64_t HW,
+                                      int64_t total_px, T* __restrict__ out_nhwc, int ld_out,
+                                      float* __restrict__ out_nchw) {
+  // one thread per pixel: NCHW reads are coalesced per channel plane, NHWC writes are ld_out wide
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total_px;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b = p / HW, s = p - b * HW;
+    for (int c = 0; c < ld_out; ++c) {
+      float r = 0.f;
+      if (c < C) {
+        float v = x[(b * C + c) * HW + s];
+        if (f64_path) {
+          // bit0: offsets are float64 (x-off promotes to f64); bit1: factors are float64
+          double num = (f64_path & 1) ? (double)v - off[c] : (double)(v - (float)off[c]);
+          double d = num / fac[c];
+          d = d < lo[c] ? lo[c] : (d > hi[c] ? hi[c] : d);   // NaN propagates like torch.clamp
+          r = (float)d;
+        } else {
+          float d = (v - (float)off[c]) / (float)fac[c];     // IEEE division, like ATen
+          float l = (float)lo[c], h = (float)hi[c];
+          r = d < l ? l : (d > h ? h : d);
+        }
+        if (out_nchw) out_nchw[(b * C + c) * HW + s] = r;
+      }
+      if (out_nhwc) out_nhwc[p * ld_out + c] = from_f<T>(r);
+    }
+  }
+}
+
+extern "C" int sc_normalize_pack(const float* x, const double* off, const double* fac, const double* lo,
+                                 const double* hi, int f64_path, int B, int C, int H, int W,
+                                 void* out_nhwc, int ld_out, int dtype, float* out_nchw, void* stream) {
+  if (!x || B <= 0 || C <= 0 || ld_out < C) return SC_ERR_BAD_ARG;
+  int64_t HW = (int64_t)H * W, total = HW * B;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  SC_DISPATCH_DTYPE(dtype, (normalize_pack_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+                               x, off, fac, lo, hi, f64_path, C, HW, total, (T*)out_nhwc, ld_out, out_nchw)));
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel reductions over NHWC pixels: thread = (pixel lane, 8-channel vector)
+// ------------------------------------------------------------------------------------------------
+struct RedGeom {
+  int CV, CVB, PL, gy;
+};
+static RedGeom red_geom(int C) {
+  RedGeom g;
+  g.CV = C / 8;
+  g.CVB = g.CV < 256 ? g.CV : 256;
+  g.PL = 256 / g.CVB;
+  g.gy = (g.CV + g.CVB - 1) / g.CVB;
+  return g;
+}
+static int red_blocks(int64_t P, int PL, int gy) {
+  int64_t want = (P + PL * 8 - 1) / (PL * 8);   // >= 8 pixels per thread
+  int64_t cap = (kNumSMs * 8) / gy;
+  if (cap < 1) cap = 1;
+  return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __restrict__ sums, int64_t P,
+                                int C, int CVB, int PL) {
+  extern __shared__ double sm[];   // [2][CVB*8]
+  int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
+  int cv = blockIdx.y * CVB + cvl;
+  for (int i = threadIdx.x; i < 2 * CVB * 8; i += blockDim.x) sm[i] = 0.0;
+  __syncthreads();
+  if (pl < PL && cv * 8 < C) {
+    double s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0;
+    for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
+      f8 v = load8<T>(y + p * ldy + cv * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double d = (double)v.v[i];
+        s[i] += d;
+        q[i] += d * d;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sm[cvl * 8 + i], s[i]);
+      atomicAdd(&sm[CVB * 8 + cvl * 8 + i], q[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CVB * 8; i += blockDim.x) {
+    int c = blockIdx.y * CVB * 8 + i;
+    if (c < C) {
+      atomicAdd(&sums[c], sm[i]);
+      atomicAdd(&sums[C + c], sm[CVB * 8 + i]);
+    }
+  }
+}
+
+extern "C" int sc_bn_stats(const void* y, int ldy, double* sums, int64_t P, int C, int dtype, void* stream) {
+  if (!y || !sums || C % 8 || ldy % 8 || P <= 0) return SC_ERR_BAD_ARG;
+  RedGeom g = red_geom(C);
+  dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
+  size_t smem = 2 * g.CVB * 8 * sizeof(double);
+  SC_DISPATCH_DTYPE(dtype, (bn_stats_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+                               (const T*)y, ldy, sums, P, C, g.CVB, g.PL)));
+  return check_launch();
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t P, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* running_mean, float* running_var, float momentum, float eps,
+                                   int training, float* scale, float* shift, float* save_mean,
+                                   float* save_invstd) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    double m = sums[c] / (double)P;
+    double var = sums[C + c] / (double)P - m * m;   // biased, used for normalisation
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (running_mean) {
+      double unb = P > 1 ? var * ((double)P / (double)(P - 1)) : var;
+      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+  } else {
+    mean = running_mean[c];
+    invstd = 1.f / sqrtf(running_var[c] + eps);
+  }
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  float sc_ = g * invstd;
+  scale[c] = sc_;
+  shift[c] = b - mean * sc_;
+  if (save_mean) save_mean[c] = mean;
+  if (save_invstd) save_invstd[c] = invstd;
+}
+
+extern "C" int sc_bn_finalize(const double* sums, int64_t P, int C, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, float momentum, float eps,
+                              int training, float* scale, float* shift, float* save_mean,
+                              float* save_invstd, void* stream) {
+  if (C <= 0 || !scale || !shift || (training && !sums) || (!training && (!running_mean || !running_var)))
+    return SC_ERR_BAD_ARG;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      sums, P, C, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift,
+      save_mean, save_invstd);
+  return check_launch();
+}
+
+template <typename T>
+__global__ void bn_act_kernel(const T* __restrict__ y, int ldy, const float* __restrict__ scale,
+                              const float* __restrict__ shift, int act, const T* __restrict__ res, int ldr,
+                              T* __restrict__ z, int ldz, int64_t total, int CV, int H, int W, int up2) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    int64_t p = idx / CV;
+    f8 v = load8<T>(y + p * ldy + cv * 8);
+    if (scale) {
+      f8 sc_ = load8<float>(scale + cv * 8), sh = load8<float>(shift + cv * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v.v[i] = apply_act(fmaf(v.v[i], sc_.v[i], sh.v[i]), act);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v.v[i] = apply_act(v.v[i], act);
+    }
+    if (res) {
+      f8 r = load8<T>(res + p * ldr + cv * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v.v[i] += r.v[i];
+    }
+    if (!up2) {
+      store8<T>(z + p * ldz + cv * 8, v);
+    } else {
+      int w = (int)(p % W);
+      int64_t t = p / W;
+      int h = (int)(t % H);
+      int64_t n = t / H;
+      int64_t base = ((n * 2 * H + 2 * h) * (2 * (int64_t)W) + 2 * w);
+      T* o = z + base * ldz + cv * 8;
+      store8<T>(o, v);
+      store8<T>(o + ldz, v);
+      store8<T>(o + (int64_t)2 * W * ldz, v);
+      store8<T>(o + ((int64_t)2 * W + 1) * ldz, v);
+    }
+  }
+}
+
+static int ew_blocks(int64_t total) {
+  int64_t b = (total + 255) / 256;
+  int64_t cap = (int64_t)kNumSMs * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+extern "C" int sc_bn_act(const void* y, int ldy, const float* scale, const float* shift, int act,
+                         const void* residual, int ldr, void* z, int ldz, int N, int H, int W, int C,
+                         int upsample2, int dtype, void* stream) {
+  if (!y || !z || C % 8 || ldy % 8 || ldz % 8 || (residual && ldr % 8)) return SC_ERR_BAD_ARG;
+  int CV = C / 8;
+  int64_t total = (int64_t)N * H * W * CV;
+  SC_DISPATCH_DTYPE(dtype, (bn_act_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)y, ldy, scale, shift, act, (const T*)residual, ldr, (T*)z, ldz,
+                               total, CV, H, W, upsample2)));
+  return check_launch();
+}
+
+// dz gather: plain or 2x2 sum-pooled from the (N,2H,2W,ld) buffer of an upsampled consumer
+template <typename T>
+__device__ __forceinline__ f8 load_dz(const T* dz, int lddz, int pooled, int64_t p, int cv, int H, int W) {
+  if (!pooled) return load8<T>(dz + p * lddz + cv * 8);
+  int w = (int)(p % W);
+  int64_t t = p / W;
+  int h = (int)(t % H);
+  int64_t n = t / H;
+  int64_t base = ((n * 2 * H + 2 * h) * (2 * (int64_t)W) + 2 * w);
+  const T* o = dz + base * lddz + cv * 8;
+  f8 a = load8<T>(o), b = load8<T>(o + lddz), c = load8<T>(o + (int64_t)2 * W * lddz),
+     d = load8<T>(o + ((int64_t)2 * W + 1) * lddz);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a.v[i] = (a.v[i] + b.v[i]) + (c.v[i] + d.v[i]);
+  return a;
+}
+
+template <typename T>
+__global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int pooled, const T* __restrict__ y,
+                                     int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                                     double* __restrict__ red, int64_t P, int C, int H, int W, int CVB, int PL) {
+  extern __shared__ double sm[];
+  int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
+  int cv = blockIdx.y * CVB + cvl;
+  for (int i = threadIdx.x; i < 2 * CVB * 8; i += blockDim.x) sm[i] = 0.0;
+  __syncthreads();
+  if (pl < PL && cv * 8 < C) {
+    f8 sc_ = load8<float>(scale + cv * 8), sh = load8<float>(shift + cv * 8);
+    f8 mu = load8<float>(mean + cv * 8), is = load8<float>(invstd + cv * 8);
+    double s[8], q[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0;
+    for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
+      f8 yv = load8<T>(y + p * ldy + cv * 8);
+      f8 g = load_dz<T>(dz, lddz, pooled, p, cv, H, W);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float gi = g.v[i] * act_mask(fmaf(yv.v[i], sc_.v[i], sh.v[i]), act);
+        float xh = (yv.v[i] - mu.v[i]) * is.v[i];
+        s[i] += (double)gi;
+        q[i] += (double)gi * (double)xh;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      atomicAdd(&sm[cvl * 8 + i], s[i]);
+      atomicAdd(&sm[CVB * 8 + cvl * 8 + i], q[i]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CVB * 8; i += blockDim.x) {
+    int c = blockIdx.y * CVB * 8 + i;
+    if (c < C) {
+      atomicAdd(&red[c], sm[i]);
+      atomicAdd(&red[C + c], sm[CVB * 8 + i]);
+    }
+  }
+}
+
+extern "C" int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void* y, int ldy,
+                                const float* scale, const float* shift, const float* mean,
+                                const float* invstd, int act, double* red, int N, int H, int W, int C,
+                                int dtype, void* stream) {
+  if (!dz || !y || !red || C % 8 || ldy % 8 || lddz % 8) return SC_ERR_BAD_ARG;
+  int64_t P = (int64_t)N * H * W;
+  RedGeom g = red_geom(C);
+  dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
+  size_t smem = 2 * g.CVB * 8 * sizeof(double);
+  SC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+                               (const T*)dz, lddz, pooled, (const T*)y, ldy, scale, shift, mean, invstd, act,
+                               red, P, C, H, W, g.CVB, g.PL)));
+  return check_launch();
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dz, int lddz, int pooled, const T* __restrict__ y,
+                                    int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, int act, const double* __restrict__ red,
+                                    T* __restrict__ dy, int lddy, float* dgamma, float* dbeta, int64_t total,
+                                    int CV, int C, int H, int W, double invP) {
+  if (blockIdx.x == 0 && dgamma) {   // parameter gradients: dbeta = sum g, dgamma = sum g*xhat
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] += (float)red[c];
+      dgamma[c] += (float)red[C + c];
+    }
+  }
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    int64_t p = idx / CV;
+    f8 sc_ = load8<float>(scale + cv * 8), sh = load8<float>(shift + cv * 8);
+    f8 mu = load8<float>(mean + cv * 8), is = load8<float>(invstd + cv * 8);
+    f8 yv = load8<T>(y + p * ldy + cv * 8);
+    f8 g = load_dz<T>(dz, lddz, pooled, p, cv, H, W);
+    f8 o;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int c = cv * 8 + i;
+      float gi = g.v[i] * act_mask(fmaf(yv.v[i], sc_.v[i], sh.v[i]), act);
+      float xh = (yv.v[i] - mu.v[i]) * is.v[i];
+      float m1 = (float)(red[c] * invP), m2 = (float)(red[C + c] * invP);
+      // gamma*invstd == scale
+      o.v[i] = sc_.v[i] * (gi - m1 - xh * m2);
+    }
+    store8<T>(dy + p * lddy + cv * 8, o);
+  }
+}
+
+extern "C" int sc_bn_bwd_apply(const void* dz, int lddz, int pooled, const void* y, int ldy,
+                               const float* scale, const float* shift, const float* mean,
+                               const float* invstd, const float* gamma, int act, const double* red,
+                               void* dy, int lddy, float* dgamma, float* dbeta, int N, int H, int W, int C,
+                               int dtype, void* stream) {
+  if (!dz || !y || !red || !dy || C % 8 || ldy % 8 || lddz % 8 || lddy % 8) return SC_ERR_BAD_ARG;
+  (void)gamma;
+  int CV = C / 8;
+  int64_t P = (int64_t)N * H * W, total = P * CV;
+  SC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)dz, lddz, pooled, (const T*)y, ldy, scale, shift, mean, invstd, gamma,
+                               act, red, (T*)dy, lddy, dgamma, dbeta, total, CV, C, H, W, 1.0 / (double)P)));
+  return check_launch();
+}
+
+template <typename T>
+__global__ void add_into_kernel(const T* __restrict__ a, int lda, int pooled, T* __restrict__ out, int ldo,
+                                int accumulate, int64_t total, int CV, int H, int W) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int cv = (int)(idx % CV);
+    int64_t p = idx / CV;
+    f8 v = load_dz<T>(a, lda, pooled, p, cv, H, W);
+    if (accumulate) {
+      f8 o = load8<T>(out + p * ldo + cv * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v.v[i] += o.v[i];
+    }
+    store8<T>(out + p * ldo + cv * 8, v);
+  }
+}
+
+extern "C" int sc_add_into(const void* a, int lda, int pooled, void* out, int ldo, int accumulate, int N,
+                           int H, int W, int C, int dtype, void* stream) {
+  if (!a || !out || C % 8 || lda % 8 || ldo % 8) return SC_ERR_BAD_ARG;
+  int CV = C / 8;
+  int64_t total = (int64_t)N * H * W * CV;
+  SC_DISPATCH_DTYPE(dtype, (add_into_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)a, lda, pooled, (T*)out, ldo, accumulate, total, CV, H, W)));
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// segmentation head: Conv2d(C->1, 3x3, pad 1, bias).  AI 8.5 FLOP/B -> one thread per pixel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHeadMaxC = 64;
+
+template <typename T>
+__global__ void head_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ w,
+                                  const float* __restrict__ bias, float* __restrict__ logits, int N, int H,
+                                  int W, int C) {
+  __shared__ float ws[9 * kHeadMaxC];   // [tap][c]
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    int tap = i / C, c = i % C;
+    ws[i] = w[c * 9 + tap];             // torch (1,C,3,3)
+  }
+  __syncthreads();
+  float b = bias ? bias[0] : 0.f;
+  int64_t total = (int64_t)N * H * W;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    int wq = (int)(p % W);
+    int64_t t = p / W;
+    int h = (int)(t % H);
+    float acc = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      int ih = h + kh - 1;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        int iw = wq + kw - 1;
+        if (iw < 0 || iw >= W) continue;
+        const T* xp = x + (p + (int64_t)(kh - 1) * W + (kw - 1)) * ldx;
+        const float* wp = ws + (kh * 3 + kw) * C;
+        for (int c = 0; c < C; c += 8) {
+          f8 v = load8<T>(xp + c);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc = fmaf(v.v[i], wp[c + i], acc);
+        }
+      }
+    }
+    logits[p] = acc + b;
+  }
+}
+
+extern "C" int sc_head_fprop(const void* x, int ldx, const float* w, const float* bias, float* logits, int N,
+                             int H, int W, int C, int dtype, void* stream) {
+  if (!x || !w || !logits || C % 8 || C > kHeadMaxC || ldx % 8) return SC_ERR_BAD_ARG;
+  int64_t total = (int64_t)N * H * W;
+  SC_DISPATCH_DTYPE(dtype, (head_fprop_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)x, ldx, w, bias, logits, N, H, W, C)));
+  return check_launch();
+}
+
+template <typename T>
+__global__ void head_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dl, T* __restrict__ dx,
+                                  int lddx, int N, int H, int W, int C) {
+  __shared__ float ws[9 * kHeadMaxC];
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    int tap = i / C, c = i % C;
+    ws[i] = w[c * 9 + tap];
+  }
+  __syncthreads();
+  int64_t total = (int64_t)N * H * W;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total;
+       p += (int64_t)gridDim.x * blockDim.x) {
+    int wq = (int)(p % W);
+    int64_t t = p / W;
+    int h = (int)(t % H);
+    float g[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        // dx[h,w] += dl[h-kh+1, w-kw+1] * w[kh,kw]
+        int oh = h - kh + 1, ow = wq - kw + 1;
+        g[kh * 3 + kw] = (oh >= 0 && oh < H && ow >= 0 && ow < W) ? dl[p + (int64_t)(1 - kh) * W + (1 - kw)] : 0.f;
+      }
+    for (int c = 0; c < C; c += 8) {
+      f8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float a = 0.f;
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) a = fmaf(g[tp], ws[tp * C + c + i], a);
+        o.v[i] = a;
+      }
+      store8<T>(dx + p * lddx + c, o);
+    }
+  }
+}
+
+template <typename T>
+__global__ void head_wgrad_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ dl,
+                                  float* __restrict__ dw, float* __restrict__ dbias, int N, int H, int W, int C) {
+  // thread = (pixel lane, 8-channel vector); 72 fp32 partials per thread, block-reduced in smem
+  __shared__ float sm[9 * kHeadMaxC + 1];
+  int CV = C / 8, PL = blockDim.x / CV;
+  int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
+  for (int i = threadIdx.x; i < 9 * C + 1; i += blockDim.x) sm[i] = 0.f;
+  __syncthreads();
+  float acc[9][8];
+  float bsum = 0.f;
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[tp][i] = 0.f;
+  int64_t total = (int64_t)N * H * W;
+  if (pl < PL) {
+    for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < total; p += (int64_t)gridDim.x * PL) {
+      int wq = (int)(p % W);
+      int64_t t = p / W;
+      int h = (int)(t % H);
+      float g = dl[p];
+      if (cv == 0) bsum += g;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        int ih = h + kh - 1;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          int iw = wq + kw - 1;
+          if (iw < 0 || iw >= W) continue;
+          f8 v = load8<T>(x + (p + (int64_t)(kh - 1) * W + (kw - 1)) * ldx + cv * 8);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[kh * 3 + kw][i] = fmaf(v.v[i], g, acc[kh * 3 + kw][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sm[tp * C + cv * 8 + i], acc[tp][i]);
+    if (cv == 0) atomicAdd(&sm[9 * C], bsum);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    int tap = i / C, c = i % C;
+    atomicAdd(&dw[c * 9 + tap], sm[i]);
+  }
+  if (threadIdx.x == 0 && dbias) atomicAdd(dbias, sm[9 * C]);
+}
+
+extern "C" int sc_head_bwd(const void* x, int ldx, const float* w, const float* dlogits, void* dx, int lddx,
+                           float* dw, float* dbias, int N, int H, int W, int C, int dtype, void* stream) {
+  if (!x || !w || !dlogits || C % 8 || C > kHeadMaxC || ldx % 8) return SC_ERR_BAD_ARG;
+  int64_t total = (int64_t)N * H * W;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dx) {
+    if (lddx % 8) return SC_ERR_BAD_ARG;
+    SC_DISPATCH_DTYPE(dtype, (head_dgrad_kernel<T><<<ew_blocks(total), 256, 0, st>>>(w, dlogits, (T*)dx, lddx, N, H, W, C)));
+  }
+  if (dw) {
+    int PL = 256 / (C / 8);
+    int blocks = (int)((total + PL * 16 - 1) / (PL * 16));
+    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+    if (blocks < 1) blocks = 1;
+    SC_DISPATCH_DTYPE(dtype, (head_wgrad_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, ldx, dlogits, dw, dbias, N, H, W, C)));
+  }
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// A3/A4/A6: fused weighted BCE-with-logits + gradient + decisions + confusion counts
+// ------------------------------------------------------------------------------------------------
+__global__ void bce_fused_kernel(const float* __restrict__ logits, const float* __restrict__ y,
+                                 const float* __restrict__ w, float pw, int64_t HW, float grad_scale,
+                                 double* loss_sum, float* __restrict__ grad, long long* cm, long long* pred_count,
+                                 long long* cm_sig, long long* pred_count_sig, float* __restrict__ prediction,
+                                 float* __restrict__ loss_px, float* __restrict__ loss_px_w,
+                                 long long* __restrict__ pred_binary, long long* __restrict__ differences) {
+  int b = blockIdx.y;
+  const int64_t base = (int64_t)b * HW;
+  double lsum = 0.0;
+  long long c_val[4] = {0, 0, 0, 0}, c_sig[4] = {0, 0, 0, 0};
+  for (int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; s < HW; s += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = base + s;
+    float x = logits[i], t = y[i], wt = w ? w[i] : 1.f;
+    // ATen: (1-t)*x + (1+(pw-1)*t) * (log1p(exp(-|x|)) + max(-x,0))
+    float lw = 1.f + (pw - 1.f) * t;
+    float l = (1.f - t) * x + lw * (log1pf(expf(-fabsf(x))) + fmaxf(-x, 0.f));
+    lsum += (double)(l * wt);
+    // sigmoid as ATen computes it: 1/(1+exp(-x))
+    float sg = 1.f / (1.f + expf(-x));
+    if (grad) {
+      float tt = pw * t;
+      grad[i] = ((tt + 1.f - t) * sg - tt) * wt * grad_scale;
+    }
+    int ti = (int)(long long)t;              // y.long()
+    int pv = x >= 0.f ? 1 : 0;               // model_module.py:124
+    int ps = sg > 0.5f ? 1 : 0;              // model_module.py:204
+    if (ti == 0 || ti == 1) {
+      c_val[2 * ti + pv]++;
+      c_sig[2 * ti + ps]++;
+    }
+    if (prediction) prediction[i] = sg;
+    if (loss_px) loss_px[i] = l;
+    if (loss_px_w) loss_px_w[i] = wt * l;
+    if (pred_binary) pred_binary[i] = ps;
+    if (differences) differences[i] = 2 * ps + (t == 1.f ? 1 : 0);   // model_module.py:268-269
+  }
+  __shared__ double s_l;
+  __shared__ long long s_c[8];
+  if (threadIdx.x == 0) s_l = 0.0;
+  if (threadIdx.x < 8) s_c[threadIdx.x] = 0;
+  __syncthreads();
+  lsum = warp_sum(lsum);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    c_val[k] = warp_sum(c_val[k]);
+    c_sig[k] = warp_sum(c_sig[k]);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&s_l, lsum);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      atomicAdd((unsigned long long*)&s_c[k], (unsigned long long)c_val[k]);
+      atomicAdd((unsigned long long*)&s_c[4 + k], (unsigned long long)c_sig[k]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (loss_sum) atomicAdd(loss_sum, s_l);
+    if (cm)
+      for (int k = 0; k < 4; ++k) atomicAdd((unsigned long long*)&cm[k], (unsigned long long)s_c[k]);
+    if (cm_sig)
+      for (int k = 0; k < 4; ++k) atomicAdd((unsigned long long*)&cm_sig[k], (unsigned long long)s_c[4 + k]);
+    if (pred_count) atomicAdd((unsigned long long*)&pred_count[b], (unsigned long long)(s_c[1] + s_c[3]));
+    if (pred_count_sig) atomicAdd((unsigned long long*)&pred_count_sig[b], (unsigned long long)(s_c[5] + s_c[7]));
+  }
+}
+
+extern "C" int sc_bce_fused(const float* logits, const float* y, const float* w, float pos_weight, int B,
+                            int64_t HW, float grad_scale, double* loss_sum, float* grad, int64_t* cm,
+                            int64_t* pred_count, int64_t* cm_sig, int64_t* pred_count_sig, float* prediction,
+                            float* loss_px, float* loss_px_w, int64_t* pred_binary, int64_t* differences,
+                            void* stream) {
+  if (!logits || !y || B <= 0 || HW <= 0) return SC_ERR_BAD_ARG;
+  int bx = (int)((HW + 1023) / 1024);
+  int cap = (kNumSMs * 8 + B - 1) / B;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, B);
+  bce_fused_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+      logits, y, w, pos_weight, HW, grad_scale, loss_sum, grad, (long long*)cm, (long long*)pred_count,
+      (long long*)cm_sig, (long long*)pred_count_sig, prediction, loss_px, loss_px_w, (long long*)pred_binary,
+      (long long*)differences);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// A16 Adam (torch.optim.Adam defaults: no weight decay, no amsgrad), one flat arena
+// ------------------------------------------------------------------------------------------------
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt, float gs) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gs;
+    float mi = m[i] + (gi - m[i]) * (1.f - b1);          // torch: exp_avg.lerp_(grad, 1-beta1)
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;          // exp_avg_sq.mul_(b2).addcmul_(g,g,1-b2)
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - (lr / bc1) * (mi / denom);
+  }
+}
+
+extern "C" int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                            float beta2, float eps, int step_host, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || n <= 0 || step_host < 1) return SC_ERR_BAD_ARG;
+  float bc1 = 1.f - powf(beta1, (float)step_host);
+  float bc2 = 1.f - powf(beta2, (float)step_host);
+  adam_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1,
+                                                               sqrtf(bc2), grad_scale);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: OIHW f32 -> [tap][Cin][Cout] f32 (optionally the flipped/transposed data-gradient filter)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cin,
+                                    int KK, int flip_t) {
+  int64_t total = (int64_t)Cout * Cin * KK;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    if (!flip_t) {
+      // o[tap][ci][co] = w[co][ci][tap]
+      int co = (int)(i % Cout);
+      int64_t t = i / Cout;
+      int ci = (int)(t % Cin);
+      int tap = (int)(t / Cin);
+      o[i] = w[((int64_t)co * Cin + ci) * KK + tap];
+    } else {
+      // dgrad filter: input channels = Cout, output channels = Cin: o[tap][co][ci] = w[co][ci][KK-1-tap]
+      int ci = (int)(i % Cin);
+      int64_t t = i / Cin;
+      int co = (int)(t % Cout);
+      int tap = (int)(t / Cout);
+      o[i] = w[((int64_t)co * Cin + ci) * KK + (KK - 1 - tap)];
+    }
+  }
+}
+
+extern "C" int sc_pack_weights(const float* w_oihw, float* w_packed, int Cout, int Cin, int KH, int KW,
+                               int flip_transpose, void* stream) {
+  if (!w_oihw || !w_packed) return SC_ERR_BAD_ARG;
+  int64_t total = (int64_t)Cout * Cin * KH * KW;
+  pack_weights_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(w_oihw, w_packed, Cout, Cin, KH * KW,
+                                                                           flip_transpose);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// A13 weight_mag1c and A14 threshold + binary opening with the 3x3 cross
+// ------------------------------------------------------------------------------------------------
+__global__ void weight_mag1c_kernel(const float* __restrict__ m, float* __restrict__ o, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v = m[i] / 400.f;                 // np.clip(mag1c/400, .1, 1)
+    o[i] = v < 0.1f ? 0.1f : (v > 1.f ? 1.f : v);
+  }
+}
+extern "C" int sc_weight_mag1c(const float* mag1c, float* out, int64_t n, void* stream) {
+  if (!mag1c || !out || n <= 0) return SC_ERR_BAD_ARG;
+  weight_mag1c_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(mag1c, out, n);
+  return check_launch();
+}
+
+// erosion: AND over the cross, out-of-image neighbours ignored (kornia "geodesic" border)
+__global__ void threshold_erode_kernel(const float* __restrict__ pred, float thr, uint8_t* __restrict__ er,
+                                       int B, int H, int W) {
+  int64_t total = (int64_t)B * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int w = (int)(i % W);
+    int h = (int)((i / W) % H);
+    bool v = pred[i] > thr;
+    if (h > 0) v = v && (pred[i - W] > thr);
+    if (h < H - 1) v = v && (pred[i + W] > thr);
+    if (w > 0) v = v && (pred[i - 1] > thr);
+    if (w < W - 1) v = v && (pred[i + 1] > thr);
+    er[i] = v ? 1 : 0;
+  }
+}
+__global__ void dilate_kernel(const uint8_t* __restrict__ er, long long* __restrict__ out, int B, int H, int W) {
+  int64_t total = (int64_t)B * H * W;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int w = (int)(i % W);
+    int h = (int)((i / W) % H);
+    bool v = er[i];
+    if (h > 0) v = v || er[i - W];
+    if (h < H - 1) v = v || er[i + W];
+    if (w > 0) v = v || er[i - 1];
+    if (w < W - 1) v = v || er[i + 1];
+    out[i] = v ? 1 : 0;
+  }
+}
+extern "C" int sc_threshold_opening(const float* pred, float threshold, int64_t* out, uint8_t* scratch, int B,
+                                    int H, int W, void* stream) {
+  if (!pred || !out || !scratch) return SC_ERR_BAD_ARG;
+  int64_t total = (int64_t)B * H * W;
+  threshold_erode_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(pred, threshold, scratch, B, H, W);
+  dilate_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(scratch, (long long*)out, B, H, W);
+  return check_launch();
+}

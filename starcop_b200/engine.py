@@ -1,0 +1,348 @@
+"""Layer schedule of the HyperSTARCOP U-Net (smp.Unet(mobilenet_v2)) over the
+C-ABI kernels: forward, hand-written backward, all buffers carved from one device arena.
+
+The graph is the reference's (model_module.py:238-251 -> segmentation_models_pytorch); the
+execution is B200-first: NHWC activations, training-mode BatchNorm split into
+statistics/finalize/apply so the normalise+activation runs fused in the consumer, the decoder's
+nearest-x2 upsample + concat fused into the producer's store, skip features written once straight
+into the decoder's concat buffers, gradients routed through channel-slice views instead of copies.
+"""
+import torch
+
+from . import _lib
+from ._lib import ACT_NONE, ACT_RELU, ACT_RELU6, SC_BF16, SC_F32, call
+
+MBV2_SETTING = [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2),
+                (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
+DECODER_CHANNELS = (256, 128, 64, 32, 16)
+BN_EPS, BN_MOMENTUM = 1e-5, 0.1
+
+
+class DT:
+    """NHWC device tensor view: base pointer, logical shape, channel stride."""
+    __slots__ = ("ptr", "N", "H", "W", "C", "ld", "esize", "grad", "grad_pooled")
+
+    def __init__(self, ptr, N, H, W, C, ld, esize):
+        self.ptr, self.N, self.H, self.W, self.C, self.ld, self.esize = ptr, N, H, W, C, ld, esize
+        self.grad = None          # DT of the same shape (may be a slice view)
+        self.grad_pooled = None   # DT (N,2H,2W,C) whose 2x2 sum-pool is this tensor's gradient
+
+    def slice(self, c0, c1):
+        return DT(self.ptr + c0 * self.esize, self.N, self.H, self.W, c1 - c0, self.ld, self.esize)
+
+    @property
+    def pixels(self):
+        return self.N * self.H * self.W
+
+
+class Arena:
+    """Chunked bump allocator over torch byte tensors.  The allocation sequence of a step is
+    deterministic, so every step sees identical addresses (CUDA-graph friendly); chunks are only
+    ever added, never freed."""
+
+    CHUNK = 1 << 30
+
+    def __init__(self, device):
+        self.device = device
+        self.chunks = []          # (tensor, base, size)
+        self.cur = 0
+        self.off = 0
+
+    def reset(self):
+        self.cur, self.off = 0, 0
+
+    @property
+    def reserved(self):
+        return sum(c[2] for c in self.chunks)
+
+    def alloc(self, nbytes, align=256):
+        nbytes = max(int(nbytes), 1)
+        while True:
+            if self.cur >= len(self.chunks):
+                size = max(self.CHUNK, (nbytes + 4095) // 4096 * 4096)
+                t = torch.empty(size, dtype=torch.uint8, device=self.device)
+                self.chunks.append((t, t.data_ptr(), size))
+            t, base, size = self.chunks[self.cur]
+            o = (self.off + align - 1) // align * align
+            if o + nbytes <= size:
+                self.off = o + nbytes
+                return base + o
+            self.cur += 1
+            self.off = 0
+
+    def zero(self, ptr, nbytes):
+        for t, base, size in self.chunks:
+            if base <= ptr < base + size:
+                t[ptr - base:ptr - base + nbytes].zero_()
+                return
+        raise _lib.StarcopB200Error("pointer not in arena")
+
+
+class UNetEngine:
+    """Runs forward / backward of the network whose parameters are the tensors in `params`
+    (name -> fp32 CUDA tensor, smp state_dict names) and buffers in `buffers`."""
+
+    def __init__(self, params, buffers, grads, in_channels, device, compute_dtype="f32"):
+        self.p, self.b, self.g = params, buffers, grads
+        self.cin = in_channels
+        self.device = device
+        self.dtype = SC_F32 if compute_dtype == "f32" else SC_BF16
+        self.esize = 4 if self.dtype == SC_F32 else 2
+        self.arena = None
+        self.tape = []
+        self.record = False
+        self.stream = 0
+
+    # ------------------------------------------------------------------ memory
+    def begin_step(self):
+        """Reset the bump allocators; the zero-initialised region (BN / reduction accumulators) is
+        cleared with ONE memset per chunk instead of one per buffer."""
+        if self.arena is None:
+            self.arena = Arena(self.device)
+            self.zarena = Arena(self.device)
+            self.zarena.CHUNK = 8 << 20
+        self.arena.reset()
+        self.zarena.reset()
+        for t, _, _ in self.zarena.chunks:
+            t.zero_()
+        self._zchunks_zeroed = len(self.zarena.chunks)
+
+    def new(self, N, H, W, C, ld=None):
+        ld = ld or C
+        return DT(self.arena.alloc(N * H * W * ld * self.esize), N, H, W, C, ld, self.esize)
+
+    def new_like(self, t):
+        return self.new(t.N, t.H, t.W, t.C)
+
+    def f32buf(self, n, zero=False, double=False):
+        nb = n * (8 if double else 4)
+        if zero:
+            first = self.zarena.cur >= len(self.zarena.chunks)
+            ptr = self.zarena.alloc(nb)
+            if first or self.zarena.cur >= self._zchunks_zeroed:
+                # chunk created after begin_step's memset: clear it once now
+                self.zarena.chunks[self.zarena.cur][0].zero_()
+                self._zchunks_zeroed = self.zarena.cur + 1
+            return ptr
+        return self.arena.alloc(nb)
+
+    # ------------------------------------------------------------------ gradient routing
+    def _grad_dst(self, x):
+        """-> (DT to write, accumulate flag); allocates the gradient buffer on first use."""
+        if x.grad is None:
+            x.grad = self.new_like(x)
+            return x.grad, 0
+        return x.grad, 1
+
+    def _alias_grad(self, x, g):
+        if x.grad is None:
+            x.grad = g
+        else:
+            call("sc_add_into", g.ptr, g.ld, 0, x.grad.ptr, x.grad.ld, 1, x.N, x.H, x.W, x.C, self.dtype, self.stream)
+
+    # ------------------------------------------------------------------ primitive layers
+    def _bn_forward(self, y, bn, training):
+        C, P = y.C, y.pixels
+        sums = self.f32buf(2 * C, zero=training, double=True) if training else 0
+        scale, shift = self.f32buf(C), self.f32buf(C)
+        mean, invstd = self.f32buf(C), self.f32buf(C)
+        if training:
+            call("sc_bn_stats", y.ptr, y.ld, sums, P, C, self.dtype, self.stream)
+        call("sc_bn_finalize", sums, P, C, self.p[bn + ".weight"].data_ptr(), self.p[bn + ".bias"].data_ptr(),
+             self.b[bn + ".running_mean"].data_ptr(), self.b[bn + ".running_var"].data_ptr(),
+             BN_MOMENTUM, BN_EPS, int(training), scale, shift, mean, invstd, self.stream)
+        return scale, shift, mean, invstd
+
+    def _bn_act(self, y, scale, shift, act, out=None, up2=False, residual=None):
+        if out is None:
+            out = self.new(y.N, y.H * (2 if up2 else 1), y.W * (2 if up2 else 1), y.C)
+        call("sc_bn_act", y.ptr, y.ld, scale, shift, act, residual.ptr if residual else 0,
+             residual.ld if residual else 0, out.ptr, out.ld, y.N, y.H, y.W, y.C, int(up2), self.dtype, self.stream)
+        return out
+
+    def _bn_backward(self, z, y, bn, stats, act, up2):
+        """gradient wrt z (plain z.grad, or pooled view when z was stored upsampled) -> dy (new DT)."""
+        scale, shift, mean, invstd = stats
+        C = y.C
+        if up2:
+            dz, pooled = z.grad_pooled, 1
+        else:
+            dz, pooled = z.grad, 0
+        assert dz is not None, f"no gradient reached BN {bn}"
+        red = self.f32buf(2 * C, zero=True, double=True)
+        call("sc_bn_bwd_reduce", dz.ptr, dz.ld, pooled, y.ptr, y.ld, scale, shift, mean, invstd, act, red,
+             y.N, y.H, y.W, C, self.dtype, self.stream)
+        dy = self.new_like(y)
+        call("sc_bn_bwd_apply", dz.ptr, dz.ld, pooled, y.ptr, y.ld, scale, shift, mean, invstd,
+             self.p[bn + ".weight"].data_ptr(), act, red, dy.ptr, dy.ld,
+             self.g[bn + ".weight"].data_ptr(), self.g[bn + ".bias"].data_ptr(),
+             y.N, y.H, y.W, C, self.dtype, self.stream)
+        return dy
+
+    def _dense_fprop(self, x, wname, k, stride, bias=None):
+        w = self.p[wname]
+        cout, cin = w.shape[0], w.shape[1]
+        assert cin == x.C, (wname, cin, x.C)
+        pad = k // 2
+        wp = self.f32buf(w.numel())
+        call("sc_pack_weights", w.data_ptr(), wp, cout, cin, k, k, 0, self.stream)
+        Ho, Wo = (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1
+        y = self.new(x.N, Ho, Wo, cout)
+        call("sc_conv_fprop", x.ptr, x.ld, wp, 0, y.ptr, y.ld, x.N, x.H, x.W, cin, cout, k, k, stride, pad,
+             self.dtype, 0, self.stream)
+        return y
+
+    def _dense_backward(self, x, dy, wname, k, stride, need_dx=True):
+        w = self.p[wname]
+        cout, cin = w.shape[0], w.shape[1]
+        pad = k // 2
+        call("sc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), x.N, x.H, x.W, cin, cout,
+             k, k, stride, pad, self.dtype, self.stream)
+        if need_dx:
+            assert stride == 1
+            wp = self.f32buf(w.numel())
+            call("sc_pack_weights", w.data_ptr(), wp, cout, cin, k, k, 1, self.stream)
+            dst, acc = self._grad_dst(x)
+            call("sc_conv_fprop", dy.ptr, dy.ld, wp, 0, dst.ptr, dst.ld, dy.N, dy.H, dy.W, cout, cin, k, k, 1, pad,
+                 self.dtype, acc, self.stream)
+
+    # ------------------------------------------------------------------ composite blocks
+    def conv_bn_act(self, x, wname, bn, k, stride, act, training, out=None, up2=False, residual=None, need_dx=True):
+        y = self._dense_fprop(x, wname, k, stride)
+        stats = self._bn_forward(y, bn, training)
+        z = self._bn_act(y, stats[0], stats[1], act, out=out, up2=up2, residual=residual)
+        if self.record:
+            def bwd():
+                dy = self._bn_backward(z, y, bn, stats, act, up2)
+                self._dense_backward(x, dy, wname, k, stride, need_dx)
+            self.tape.append(bwd)
+        return z
+
+    def inverted_residual(self, x, prefix, cin, cout, stride, t, training, out=None):
+        """torchvision InvertedResidual: [1x1 expand+BN+ReLU6] -> dw3x3+BN+ReLU6 -> 1x1 project+BN (+x)."""
+        hidden = cin * t
+        use_res = stride == 1 and cin == cout
+        i = 0
+        if t != 1:
+            y1 = self._dense_fprop(x, f"{prefix}.conv.0.0.weight", 1, 1)
+            bn1 = f"{prefix}.conv.0.1"
+            st1 = self._bn_forward(y1, bn1, training)
+            dw_in, dw_scale, dw_shift, dw_act = y1, st1[0], st1[1], ACT_RELU6
+            i = 1
+        else:
+            y1, st1, bn1 = None, None, None
+            dw_in, dw_scale, dw_shift, dw_act = x, 0, 0, ACT_NONE
+        wdw, bn2 = f"{prefix}.conv.{i}.0.weight", f"{prefix}.conv.{i}.1"
+        Ho, Wo = (x.H - 1) // stride + 1, (x.W - 1) // stride + 1
+        y2 = self.new(x.N, Ho, Wo, hidden)
+        call("sc_dwconv_fprop", dw_in.ptr, dw_in.ld, dw_scale, dw_shift, dw_act, self.p[wdw].data_ptr(),
+             y2.ptr, y2.ld, x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
+        st2 = self._bn_forward(y2, bn2, training)
+        z2 = self._bn_act(y2, st2[0], st2[1], ACT_RELU6)
+        wpr, bn3 = f"{prefix}.conv.{i + 1}.weight", f"{prefix}.conv.{i + 2}"
+        y3 = self._dense_fprop(z2, wpr, 1, 1)
+        st3 = self._bn_forward(y3, bn3, training)
+        z3 = self._bn_act(y3, st3[0], st3[1], ACT_NONE, out=out, residual=x if use_res else None)
+        if self.record:
+            def bwd():
+                dy3 = self._bn_backward(z3, y3, bn3, st3, ACT_NONE, False)
+                self._dense_backward(z2, dy3, wpr, 1, 1)
+                dy2 = self._bn_backward(z2, y2, bn2, st2, ACT_RELU6, False)
+                call("sc_dwconv_wgrad", dw_in.ptr, dw_in.ld, dw_scale, dw_shift, dw_act, dy2.ptr, dy2.ld,
+                     self.g[wdw].data_ptr(), x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
+                if use_res:
+                    self._alias_grad(x, z3.grad)        # d(x + f(x)) -> x gets dz3 as is
+                if t != 1:
+                    z1 = DT(0, y1.N, y1.H, y1.W, y1.C, y1.C, self.esize)   # virtual: only its gradient exists
+                    z1.grad = self.new_like(y1)
+                    call("sc_dwconv_dgrad", dy2.ptr, dy2.ld, self.p[wdw].data_ptr(), z1.grad.ptr, z1.grad.ld,
+                         x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
+                    dy1 = self._bn_backward(z1, y1, bn1, st1, ACT_RELU6, False)
+                    self._dense_backward(x, dy1, f"{prefix}.conv.0.0.weight", 1, 1)
+                else:
+                    # depthwise reads x directly: its data gradient goes to x
+                    if x.grad is None:
+                        x.grad = self.new_like(x)
+                        call("sc_dwconv_dgrad", dy2.ptr, dy2.ld, self.p[wdw].data_ptr(), x.grad.ptr, x.grad.ld,
+                             x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
+                    else:
+                        tmp = self.new_like(x)
+                        call("sc_dwconv_dgrad", dy2.ptr, dy2.ld, self.p[wdw].data_ptr(), tmp.ptr, tmp.ld,
+                             x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
+                        self._alias_grad(x, tmp)
+            self.tape.append(bwd)
+        return z3
+
+    # ------------------------------------------------------------------ whole network
+    def forward(self, x_nhwc, logits_ptr, training, record=None):
+        """x_nhwc: DT (N,H,W,Cin) normalised input; writes (N,H,W) fp32 logits.
+        training: BatchNorm uses batch statistics and updates the running ones;
+        record: keep what the backward pass needs (defaults to `training`)."""
+        self.record = training if record is None else record
+        if self.record and not training:
+            raise _lib.StarcopB200Error("backward through eval-mode BatchNorm is not implemented: call .train() before a step that needs gradients")
+        N, H, W = x_nhwc.N, x_nhwc.H, x_nhwc.W
+        assert H % 32 == 0 and W % 32 == 0, "input height and width must be divisible by 32 (smp check_input_shape)"
+        self.tape = []
+        E = "encoder.features"
+        skip_c = (16, 24, 32, 96)                          # f1..f4
+        # decoder concat buffers: [upsampled | skip], block i works at stride 16 >> i
+        cat = []
+        up_c = (1280,) + DECODER_CHANNELS[:-1]
+        for i in range(5):
+            s = 16 >> i
+            cs = skip_c[3 - i] if i < 4 else 0
+            cat.append(self.new(N, H // s, W // s, up_c[i] + cs))
+        skip_dst = {1: cat[3].slice(up_c[3], up_c[3] + 16), 3: cat[2].slice(up_c[2], up_c[2] + 24),
+                    6: cat[1].slice(up_c[1], up_c[1] + 32), 13: cat[0].slice(up_c[0], up_c[0] + 96)}
+
+        skip_obj, up_src = {}, {}
+        # ---- encoder
+        x = self.conv_bn_act(x_nhwc, f"{E}.0.0.weight", f"{E}.0.1", 3, 2, ACT_RELU6, training, need_dx=False)
+        idx, cin = 1, 32
+        for t, c, n, s in MBV2_SETTING:
+            for r in range(n):
+                x = self.inverted_residual(x, f"{E}.{idx}", cin, c, s if r == 0 else 1, t, training,
+                                           out=skip_dst.get(idx))
+                if idx in skip_dst:
+                    skip_obj[idx] = x
+                cin = c
+                idx += 1
+        # features.18 (1x1 320->1280) stored upsampled x2 straight into cat[0][:, :1280]
+        up_src[0] = self.conv_bn_act(x, f"{E}.18.0.weight", f"{E}.18.1", 1, 1, ACT_RELU6, training,
+                                     out=cat[0].slice(0, 1280), up2=True)
+        skip_of_block = {0: 13, 1: 6, 2: 3, 3: 1}
+        # ---- decoder
+        for i in range(5):
+            D = f"decoder.blocks.{i}"
+            if self.record:
+                def route(ci=cat[i], cup=up_c[i], src=up_src[i], skip=skip_obj.get(skip_of_block.get(i))):
+                    # split d(cat) into the pooled gradient of the upsampled producer and the skip's gradient
+                    g = ci.grad
+                    src.grad_pooled = g.slice(0, cup)
+                    if skip is not None:
+                        self._alias_grad(skip, g.slice(cup, ci.C))
+                self.tape.append(route)
+            z = self.conv_bn_act(cat[i], f"{D}.conv1.0.weight", f"{D}.conv1.1", 3, 1, ACT_RELU, training)
+            if i < 4:
+                up_src[i + 1] = self.conv_bn_act(z, f"{D}.conv2.0.weight", f"{D}.conv2.1", 3, 1, ACT_RELU, training,
+                                                 out=cat[i + 1].slice(0, DECODER_CHANNELS[i]), up2=True)
+            else:
+                z = self.conv_bn_act(z, f"{D}.conv2.0.weight", f"{D}.conv2.1", 3, 1, ACT_RELU, training)
+        # ---- head
+        hw, hb = self.p["segmentation_head.0.weight"], self.p["segmentation_head.0.bias"]
+        call("sc_head_fprop", z.ptr, z.ld, hw.data_ptr(), hb.data_ptr(), logits_ptr, N, H, W, z.C, self.dtype, self.stream)
+        if self.record:
+            self._head_in = z
+        return cat
+
+    def backward(self, dlogits_ptr):
+        z = self._head_in
+        z.grad = self.new_like(z)
+        hw = self.p["segmentation_head.0.weight"]
+        call("sc_head_bwd", z.ptr, z.ld, hw.data_ptr(), dlogits_ptr, z.grad.ptr, z.grad.ld,
+             self.g["segmentation_head.0.weight"].data_ptr(), self.g["segmentation_head.0.bias"].data_ptr(),
+             z.N, z.H, z.W, z.C, self.dtype, self.stream)
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = []

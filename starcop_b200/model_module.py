@@ -1,0 +1,484 @@
+"""Drop-in for ``starcop.models.model_module`` (reference file:line cited per method).
+
+``ModelModule`` keeps the reference's LightningModule method surface, constructor signature
+(``ModelModule(settings)``), batch-dict contract and state_dict key layout; everything it computes
+runs in the hand-written CUDA kernels behind ``include/starcop_b200.h``.  When
+``pytorch_lightning`` is importable the class derives from ``pl.LightningModule`` so the
+reference's ``Trainer.fit(model, data_module)`` (scripts/train.py:140) accepts it unchanged;
+otherwise it is a plain ``torch.nn.Module`` with the same methods.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import metrics
+from .engine import DT, UNetEngine
+from .network import UnetParameters
+from .normalizer import DataNormalizer
+
+try:                                                       # pragma: no cover - not in this image
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+except Exception:                                          # noqa: BLE001
+    pl = None
+    _Base = torch.nn.Module
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# --------------------------------------------------------------------------------------------------
+# network: parameters in one flat fp32 arena + the CUDA engine
+# --------------------------------------------------------------------------------------------------
+class _UnetFunction(torch.autograd.Function):
+    """logits = network(x): one autograd node for the whole U-Net; backward = the engine's
+    hand-written backward pass, gradients delivered as views of the flat gradient arena."""
+
+    @staticmethod
+    def forward(ctx, net, x, norm, *params):
+        ctx.net = net
+        ctx.training = True
+        return net._forward_impl(x, norm, net.training, record=True)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        net = ctx.net
+        net._backward_impl(dlogits)
+        return (None, None, None, *net._grad_views)
+
+
+class HyperStarcopUnet(UnetParameters):
+    """``smp.Unet(mobilenet_v2, in_channels=C, classes=1)`` executed by the sm_100a kernels.
+
+    compute_dtype "f32": fp32 activations + fp32-FMA convolutions (the parity mode: the
+    reference trains in fp32, scripts/train.py:120-138).  "bf16": bf16 activations, tcgen05
+    tensor-core convolutions with fp32 accumulation (BASELINE.json's throughput mode).
+    """
+
+    def __init__(self, in_channels, classes=1, compute_dtype="f32"):
+        super().__init__(in_channels, classes)
+        self.compute_dtype = compute_dtype
+        self._engine = None
+        self._flat = None
+        self._names = [n for n, _ in self.named_parameters()]
+
+    # ---- flat parameter / gradient arenas ---------------------------------------------------
+    def _materialize(self):
+        params = list(self.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise _lib.StarcopB200Error("starcop_b200 runs on CUDA only: move the module to a GPU (no CPU path)")
+        ok = self._flat is not None and self._flat[0].device == dev
+        if ok:
+            off = 0
+            base = self._flat[0].data_ptr()
+            for p in params:
+                if p.data_ptr() != base + off * 4:
+                    ok = False
+                    break
+                off += (p.numel() + 3) // 4 * 4
+        if ok:
+            return
+        sizes = [(p.numel() + 3) // 4 * 4 for p in params]          # 16 B aligned slices
+        total = sum(sizes)
+        flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
+        flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        views, off = [], 0
+        for p, s in zip(params, sizes):
+            flat_p[off:off + p.numel()].copy_(p.data.reshape(-1).float())
+            p.data = flat_p[off:off + p.numel()].view(p.shape)
+            views.append(flat_g[off:off + p.numel()].view(p.shape))
+            off += s
+        self._flat = (flat_p, flat_g)
+        self._grad_views = views
+        pd = {n: p.data for n, p in self.named_parameters()}
+        gd = dict(zip(self._names, views))
+        bd = {n: b for n, b in self.named_buffers()}
+        self._engine = UNetEngine(pd, bd, gd, self.in_channels, dev, self.compute_dtype)
+        self._adam_state = None
+
+    @property
+    def flat_params(self):
+        self._materialize()
+        return self._flat[0]
+
+    @property
+    def flat_grads(self):
+        self._materialize()
+        return self._flat[1]
+
+    # ---- forward / backward -------------------------------------------------------------------
+    def _forward_impl(self, x, norm, training, record=None):
+        self._materialize()
+        eng = self._engine
+        x = x.contiguous().float()
+        B, C, H, W = x.shape
+        assert C == self.in_channels, f"expected {self.in_channels} input channels, got {C}"
+        if H % 32 or W % 32:                     # smp check_input_shape
+            raise RuntimeError(f"Wrong input shape height={H}, width={W}. Expected image height and width "
+                               f"divisible by 32.")
+        eng.stream = _stream(x.device)
+        eng.begin_step()
+        ldin = C if eng.dtype == _lib.SC_F32 else (C + 7) // 8 * 8
+        xin = eng.new(B, H, W, C, ld=ldin)
+        if norm is None:
+            prm, mask = self._identity_norm(x.device, C), 0
+        else:
+            prm, mask = norm
+        _lib.call("sc_normalize_pack", x.data_ptr(), prm[0].data_ptr(), prm[1].data_ptr(), prm[2].data_ptr(),
+                  prm[3].data_ptr(), mask, B, C, H, W, xin.ptr, ldin, eng.dtype, 0, eng.stream)
+        logits = torch.empty(B, 1, H, W, dtype=torch.float32, device=x.device)
+        eng.forward(xin, logits.data_ptr(), training, record)
+        if training:
+            if getattr(self, "_nbt", None) is None or self._nbt[0].device != x.device:
+                self._nbt = [b for n, b in self.named_buffers() if n.endswith("num_batches_tracked")]
+            torch._foreach_add_(self._nbt, 1)
+        return logits
+
+    def _backward_impl(self, dlogits):
+        eng = self._engine
+        self._flat[1].zero_()
+        d = dlogits.contiguous().float()
+        eng.stream = _stream(d.device)
+        eng.backward(d.data_ptr())
+
+    def _identity_norm(self, device, C):
+        key = (str(device), C)
+        if getattr(self, "_idn", None) is None or self._idn[0] != key:
+            big = torch.finfo(torch.float32).max
+            arr = torch.tensor([[0.] * C, [1.] * C, [-big] * C, [big] * C], dtype=torch.float64, device=device)
+            self._idn = (key, arr)
+        return self._idn[1]
+
+    def forward(self, x, _norm=None):
+        """x: (B,C,H,W) normalised input -> (B,1,H,W) logits (the ``self.network(...)`` call of
+        model_module.py:98).  ``_norm`` lets ModelModule fuse normalize_x into the input pack."""
+        squeeze = x.dim() == 3
+        if squeeze:
+            x = x[None]
+        params = list(self.parameters())
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if need_grad:
+            out = _UnetFunction.apply(self, x, _norm, *params)
+        else:
+            with torch.no_grad():
+                out = self._forward_impl(x, _norm, self.training, record=False)
+        return out[0] if squeeze else out
+
+    # ---- fused optimiser (Adam on the flat arena) -----------------------------------------------
+    def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        self._materialize()
+        p, g = self._flat
+        if self._adam_state is None:
+            self._adam_state = [torch.zeros_like(p), torch.zeros_like(p), 0]
+        m, v, _ = self._adam_state
+        self._adam_state[2] += 1
+        _lib.call("sc_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
+                  betas[0], betas[1], eps, self._adam_state[2], grad_scale, _stream(p.device))
+
+
+# --------------------------------------------------------------------------------------------------
+# loss: BCEWithLogitsLoss(pos_weight, reduction) + mean(loss * weight_loss), one fused kernel
+# --------------------------------------------------------------------------------------------------
+class _WeightedBCEFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, y, w, pos_weight):
+        lg = logits.contiguous().float()
+        B = lg.shape[0]
+        HW = lg.numel() // B
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=lg.device)
+        grad = torch.empty_like(lg) if ctx.needs_input_grad[0] else None
+        _lib.call("sc_bce_fused", lg.data_ptr(), y.contiguous().float().data_ptr(),
+                  w.contiguous().float().data_ptr() if w is not None else 0, float(pos_weight), B, HW,
+                  1.0 / lg.numel(), loss_sum.data_ptr(), grad.data_ptr() if grad is not None else 0,
+                  0, 0, 0, 0, 0, 0, 0, 0, 0, _stream(lg.device))
+        ctx.save_for_backward(grad)
+        return (loss_sum / lg.numel()).float()[0]
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return grad * gout, None, None, None
+
+
+class BCEWithLogitsLoss(torch.nn.Module):
+    """``torch.nn.BCEWithLogitsLoss(pos_weight=..., reduction=...)`` of model_module.py:57-58 on the
+    fused kernel.  reduction="none" returns the per-pixel loss (used by batch_with_preds :202)."""
+
+    def __init__(self, pos_weight, reduction="none"):
+        super().__init__()
+        self.pos_weight = pos_weight          # the module's own Parameter -> "loss_function.pos_weight"
+        self.reduction = reduction
+
+    def forward(self, logits, target):
+        if self.reduction == "mean":
+            return _WeightedBCEFunction.apply(logits, target, None, self.pos_weight)
+        lg = logits.detach().contiguous().float()
+        B = lg.shape[0]
+        out = torch.empty_like(lg)
+        _lib.call("sc_bce_fused", lg.data_ptr(), target.contiguous().float().data_ptr(), 0, float(self.pos_weight),
+                  B, lg.numel() // B, 0.0, 0, 0, 0, 0, 0, 0, 0, out.data_ptr(), 0, 0, 0, _stream(lg.device))
+        return out
+
+
+def weighted_bce(logits, y, weight_loss, pos_weight):
+    """torch.mean(BCEWithLogitsLoss(reduction="none")(logits, y) * weight_loss) -- model_module.py:76-79."""
+    return _WeightedBCEFunction.apply(logits, y, weight_loss, pos_weight)
+
+
+class BinaryConfusionMatrix(torch.nn.Module):
+    """torchmetrics.ConfusionMatrix(num_classes=2, task="binary") surface used by the reference
+    (update / compute / reset, model_module.py:62-63,128,135,149-163): cm[target, pred], int64."""
+
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("confmat", torch.zeros(2, 2, dtype=torch.long), persistent=False)
+
+    def update(self, preds, target):
+        idx = 2 * target.long().flatten() + preds.long().flatten()
+        self.confmat += torch.bincount(idx, minlength=4).reshape(2, 2)
+
+    def add_counts(self, counts):
+        self.confmat += counts.reshape(2, 2)
+
+    def compute(self):
+        return self.confmat.clone()
+
+    def reset(self):
+        self.confmat.zero_()
+
+    def forward(self, preds, target):
+        before = self.confmat.clone()
+        self.update(preds, target)
+        return self.confmat - before
+
+
+def pred_classification(pred_binary):
+    """model_module.py:210-212."""
+    n_pixels = (10 * np.prod(tuple(pred_binary.shape[-2:]))) / (64 ** 2)
+    return (torch.sum(pred_binary, dim=(-1, -2)) > n_pixels).long()
+
+
+def differences(y_pred_binary, y_gt):
+    """model_module.py:268-269."""
+    return 2 * y_pred_binary.long() + (y_gt == 1).long()
+
+
+def configure_architecture(architecture, num_channels, num_classes, extra_settings_model):
+    """model_module.py:224-256: the only constructible architecture is smp.Unet(mobilenet_v2)."""
+    if architecture == "unet_semseg":
+        backbone = extra_settings_model.semseg_backbone
+        if backbone != "mobilenet_v2":
+            raise Exception(f"No B200 kernel schedule for backbone: {backbone} (HyperSTARCOP uses mobilenet_v2)")
+        compute_dtype = extra_settings_model.get("compute_dtype", "f32") if hasattr(extra_settings_model, "get") \
+            else getattr(extra_settings_model, "compute_dtype", "f32")
+        # the reference loads imagenet encoder weights when num_channels == 3 (model_module.py:242);
+        # there is no network here, so a 3-channel model starts from the torchvision initialiser
+        return HyperStarcopUnet(num_channels, num_classes, compute_dtype=compute_dtype)
+    raise Exception(f"No model implemented for model_type: {architecture}")
+
+
+def load_weights(path_weights, map_location="cpu"):
+    """model_module.py:258-266 (local paths; the reference goes through fsspec for gs://)."""
+    if os.path.exists(path_weights):
+        return torch.load(path_weights, map_location=map_location)
+    raise ValueError(f"Pretrained weights file: {path_weights} does not exists")
+
+
+class ModelModule(_Base):
+    def __init__(self, settings):
+        super().__init__()
+        if hasattr(self, "save_hyperparameters") and pl is not None:
+            self.save_hyperparameters()
+        self.settings_model = settings.model
+        self.settings_wandb = getattr(settings, "wandb", None)
+        self.normalizer = DataNormalizer(settings)
+        self.num_classes = self.settings_model.num_classes
+        self.num_channels = len(settings.dataset.input_products)
+        self.network = configure_architecture(self.settings_model.model_type, self.num_channels,
+                                              self.num_classes, self.settings_model)
+        self.lr = self.settings_model.lr
+        self.lr_decay = self.settings_model.lr_decay
+        self.lr_patience = self.settings_model.lr_patience
+        self.loss_name = self.settings_model.loss
+        use_weight_loss = "use_weight_loss" not in settings.dataset or settings.dataset.use_weight_loss
+        if self.settings_model.loss == "BCEWithLogitsLoss":
+            self.reduction = "none" if use_weight_loss else "mean"
+            self.pos_weight = torch.nn.Parameter(torch.tensor(float(self.settings_model.pos_weight)),
+                                                 requires_grad=False)
+            self.loss_function = BCEWithLogitsLoss(self.pos_weight, self.reduction)
+        else:
+            raise NotImplementedError("l1 / mse belong to the regression module (out of the hot path)")
+        if self.settings_model.model_mode == "segmentation_output":
+            self.confusion_matrix = BinaryConfusionMatrix()
+            self.classification_confusion_matrix = BinaryConfusionMatrix()
+        elif self.settings_model.model_mode == "regression_output":
+            raise NotImplementedError("Not implemented yet")
+        self._logged = {}
+
+    # ---- LightningModule surface when pytorch_lightning is absent --------------------------------
+    if pl is None:
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+        def log(self, name, value, *args, **kwargs):
+            self._logged[name] = value
+
+        @classmethod
+        def load_from_checkpoint(cls, path, settings=None, map_location="cpu", **kw):
+            ckpt = torch.load(path, map_location=map_location)
+            model = cls(settings)
+            model.load_state_dict(ckpt["state_dict"] if "state_dict" in ckpt else ckpt)
+            return model
+    else:                                                  # pragma: no cover
+        def log(self, *args, **kwargs):                    # model_module.py:103-107
+            try:
+                super().log(*args, **kwargs)
+            except Exception as e:                         # noqa: BLE001
+                print(f"Bug logging {e}")
+
+    # ---- hot path -----------------------------------------------------------------------------------
+    def forward(self, x):
+        """model_module.py:90-98: network(normalizer.normalize_x(x)); the normalisation is fused
+        into the kernel that packs the input to NHWC."""
+        if not x.is_cuda:
+            raise _lib.StarcopB200Error("starcop_b200 runs on CUDA tensors only (no CPU path)")
+        return self.network(x, _norm=self.normalizer.kernel_params(x.device))
+
+    def training_step(self, batch, batch_idx):
+        """model_module.py:69-88."""
+        x, y = batch["input"], batch["output"]
+        weight_loss = batch["weight_loss"] if self.reduction == "none" else None
+        predictions = self.forward(x)
+        loss = weighted_bce(predictions, self.normalizer.normalize_y(y), weight_loss, self.pos_weight)
+        if (batch_idx % 100) == 0:
+            self.log(f"train_{self.loss_name}", loss)
+        return loss
+
+    def pred_classification(self, pred_binary):
+        return pred_classification(pred_binary)
+
+    def val_step(self, batch, batch_idx, prefix="val"):
+        """model_module.py:110-135: loss, pixel confusion matrix (pred = logits >= 0) and tile
+        classification confusion matrix from ONE pass over the logits."""
+        x, y = batch["input"], batch["output"]
+        with torch.no_grad():
+            logits = self.forward(x).contiguous()
+            y = self.normalizer.normalize_y(y).contiguous().float()
+            w = batch["weight_loss"].contiguous().float() if self.reduction == "none" else None
+            B = logits.shape[0]
+            HW = logits.numel() // B
+            dev = logits.device
+            loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+            cm = torch.zeros(4, dtype=torch.long, device=dev)
+            cnt = torch.zeros(B, dtype=torch.long, device=dev)
+            _lib.call("sc_bce_fused", logits.data_ptr(), y.data_ptr(), w.data_ptr() if w is not None else 0,
+                      float(self.pos_weight), B, HW, 0.0, loss_sum.data_ptr(), 0, cm.data_ptr(), cnt.data_ptr(),
+                      0, 0, 0, 0, 0, 0, 0, _stream(dev))
+            loss = (loss_sum / logits.numel()).float()[0]
+            self.log(f"{prefix}_loss", loss, on_epoch=True)
+            if self.settings_model.model_mode == "segmentation_output":
+                self.confusion_matrix.add_counts(cm)
+                n_pixels = (10 * np.prod(tuple(logits.shape[-2:]))) / (64 ** 2)
+                pred_cls = (cnt > n_pixels).long()[:, None]
+                y_cls = batch["has_plume"][:, None]
+                self.classification_confusion_matrix.update(pred_cls, y_cls)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        return self.val_step(batch, batch_idx, prefix="val")
+
+    def test_step(self, batch, batch_idx):
+        return self.val_step(batch, batch_idx, prefix="test")
+
+    def val_epoch_end(self, outputs, prefix):
+        """model_module.py:147-164."""
+        outs = {}
+        cm = self.confusion_matrix.compute()
+        for fun in metrics.METRICS_CONFUSION_MATRIX:
+            self.log(f"{prefix}_{fun.__name__}", fun(cm))
+        self.confusion_matrix.reset()
+        if self.settings_model.model_mode == "segmentation_output":
+            cm = self.classification_confusion_matrix.compute()
+            for fun in metrics.METRICS_CONFUSION_MATRIX:
+                self.log(f"{prefix}_classification_{fun.__name__}", fun(cm))
+            self.classification_confusion_matrix.reset()
+        return outs
+
+    def validation_epoch_end(self, outputs):
+        self.val_epoch_end(outputs, prefix="val")
+
+    def test_epoch_end(self, outputs):
+        self.val_epoch_end(outputs, prefix="test")
+
+    def configure_optimizers(self):
+        """model_module.py:172-185."""
+        if self.settings_model.optimizer == "adam":
+            optimizer = torch.optim.Adam(self.network.parameters(), self.lr)
+        else:
+            raise Exception(f"No optimizer implemented for : {self.settings_model.optimizer}")
+        scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, mode="min", factor=self.lr_decay,
+                                                               patience=self.lr_patience)
+        return {"optimizer": optimizer, "lr_scheduler": scheduler, "monitor": "val_loss"}
+
+    def batch_with_preds(self, batch):
+        """model_module.py:191-208: every per-pixel product from one fused pass over the logits."""
+        with torch.no_grad():
+            x = batch["input"]
+            B, C, H, W = x.shape
+            dev = x.device
+            logits = self.forward(x).contiguous()
+            batch = batch.copy()
+            batch["input_norm"] = self.normalizer.normalize_x(x)
+            batch["output_norm"] = self.normalizer.normalize_y(batch["output"])
+            y = batch["output_norm"].contiguous().float()
+            f = lambda: torch.empty(B, 1, H, W, dtype=torch.float32, device=dev)
+            li = lambda: torch.empty(B, 1, H, W, dtype=torch.long, device=dev)
+            pred, pb, diff = f(), li(), li()
+            weighted = self.reduction == "none"
+            lpx, lpw = (f(), f()) if weighted else (None, None)
+            w = batch["weight_loss"].contiguous().float() if weighted else None
+            cnt = torch.zeros(B, dtype=torch.long, device=dev)
+            _lib.call("sc_bce_fused", logits.data_ptr(), y.data_ptr(), w.data_ptr() if weighted else 0,
+                      float(self.pos_weight), B, H * W, 0.0, 0, 0, 0, 0, 0, cnt.data_ptr(), pred.data_ptr(),
+                      lpx.data_ptr() if weighted else 0, lpw.data_ptr() if weighted else 0, pb.data_ptr(),
+                      diff.data_ptr(), _stream(dev))
+            batch["prediction"] = pred
+            batch["logits"] = logits
+            if weighted:
+                batch["loss_per_pixel"] = lpx
+                batch["loss_per_pixel_weighted"] = lpw
+            batch["pred_binary"] = pb
+            batch["differences"] = diff
+            n_pixels = (10 * H * W) / (64 ** 2)
+            batch["pred_classification"] = (cnt > n_pixels).long()[:, None]
+        return batch
+
+    # ---- fused train step (no autograd graph): forward + loss + backward + Adam -------------------
+    def train_step_fused(self, batch, lr=None, grad_sync=None):
+        """One optimisation step entirely on the engine.  Equivalent to
+        ``loss = training_step(batch); loss.backward(); Adam.step()`` of the reference loop.
+        ``grad_sync(flat_grads)`` is the data-parallel hook (NCCL all-reduce of the flat arena)."""
+        net = self.network
+        x, y = batch["input"], batch["output"]
+        w = batch["weight_loss"] if self.reduction == "none" else None
+        net.train()
+        logits = net._forward_impl(x, self.normalizer.kernel_params(x.device), True)
+        B = logits.shape[0]
+        n = logits.numel()
+        dev = logits.device
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        grad = torch.empty_like(logits)
+        _lib.call("sc_bce_fused", logits.data_ptr(), y.contiguous().float().data_ptr(),
+                  w.contiguous().float().data_ptr() if w is not None else 0, float(self.pos_weight), B, n // B,
+                  1.0 / n, loss_sum.data_ptr(), grad.data_ptr(), 0, 0, 0, 0, 0, 0, 0, 0, 0, _stream(dev))
+        net._backward_impl(grad)
+        scale = 1.0
+        if grad_sync is not None:
+            scale = grad_sync(net.flat_grads)
+        net.adam_step(self.lr if lr is None else lr, grad_scale=scale)
+        return (loss_sum / n).float()[0]

@@ -1,0 +1,72 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, host logic."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from starcop_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "starcop_b200.h")).read()
+    declared = set(re.findall(r"\b(sc_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/starcop_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.sc_abi_version() == 1
+
+
+def test_product_does_not_import_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "starcop_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_no_cpu_path():
+    from starcop_b200 import _lib
+    from starcop_b200.model_setup import get_model
+    from starcop_b200.settings import default_settings
+    m = get_model(default_settings(), None)
+    with pytest.raises(_lib.StarcopB200Error):
+        m(torch.zeros(1, 4, 32, 32))
+
+
+def test_state_dict_keys_and_init_match_oracle():
+    from oracle.module import get_model as og
+    from starcop_b200.model_setup import get_model
+    from starcop_b200.settings import default_settings
+    torch.manual_seed(7); m = get_model(default_settings(), None)
+    torch.manual_seed(7); o = og(default_settings())
+    sm, so = m.network.state_dict(), o.network.state_dict()
+    assert list(sm) == list(so)
+    assert all(torch.equal(sm[k], so[k]) for k in sm)
+    extra = [k for k in m.state_dict() if not k.startswith("network.")]
+    assert set(extra) == {"pos_weight", "loss_function.pos_weight", "normalizer.offsets_input",
+                          "normalizer.factors_input", "normalizer.clip_min_input", "normalizer.clip_max_input"}
+    assert m.normalizer.factors_input.dtype == torch.int64        # python ints -> int64
+
+
+def test_metrics_match_reference_golden(golden):
+    from starcop_b200 import metrics
+    g = golden("metrics.npz")
+    for cm, vals in zip(g["cms"], g["values"]):
+        for n, v in zip(g["names"], vals):
+            got = float(getattr(metrics, str(n))(torch.from_numpy(cm)))
+            assert (np.isnan(got) and np.isnan(v)) or got == v, (cm, n, got, v)
+
+
+def test_synthetic_batch_contract():
+    from starcop_b200 import synthetic
+    b = synthetic.hyperstarcop_batch(4, size=64, seed=0)
+    assert b["input"].shape == (4, 4, 64, 64) and b["input"].dtype == torch.float32
+    assert b["output"].shape == (4, 1, 64, 64) and set(b["output"].unique().tolist()) <= {0.0, 1.0}
+    assert b["weight_loss"].min() >= 0.1 and b["weight_loss"].max() <= 1.0
+    assert b["has_plume"].dtype == torch.int64 and len(b["id"]) == 4
