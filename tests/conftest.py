@@ -9,6 +9,16 @@ if ROOT not in sys.path:
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 
+def pytest_sessionstart(session):
+    # the PyTorch side of every GPU parity test must be true fp32 (cuDNN would otherwise use TF32)
+    try:
+        import torch
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    except Exception:      # noqa: BLE001
+        pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
