@@ -1,0 +1,561 @@
+// tcgen05 tensor-core convolutions for the HyperSTARCOP U-Net (bf16 storage, fp32 accumulate in TMEM).
+//
+// fprop / dgrad:  implicit GEMM, M = 128 output pixels (an 8 x 16 spatial patch), N = Cout tile,
+//   K = taps x Cin.  The A tile of filter tap (dy,dx) is ONE TMA box of the NHWC activation tensor
+//   shifted by (dy,dx); out-of-image elements are zero-filled by TMA, which IS the conv padding.
+//   B = packed bf16 weights [Cout][tap][Cin] (K-major).  Warp-specialised, persistent:
+//   warp 0 TMA producer, warp 1 MMA issuer (single thread) + TMEM owner, warps 2..5 epilogue;
+//   smem ring of `stages` (A,B) tiles, two TMEM accumulator stages so the epilogue of tile i
+//   overlaps the MMAs of tile i+1.
+// wgrad:  dW[(tap,ci)][co] = sum_pixels X[pixel@tap][ci] * dY[pixel][co]; both operands are read in
+//   their natural NHWC layout as MN-major UMMA operands (the reduction runs over pixels), M = 128
+//   rows made of 128/KC shifted activation boxes, split over pixels across CTAs, fp32 atomics into
+//   the torch-layout gradient.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace sc;
+using namespace tc;
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time libcuda dependency)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                          : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// NHWC bf16 activation tensor (C, W, H, N) with channel stride ld; box = (kc, bw, bh, 1)
+static int encode_act(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int ld, int kc, int bw, int bh) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return SC_ERR_NO_DEVICE;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SC_OK : SC_ERR_BAD_ARG;
+}
+// row-major bf16 matrix (cols, rows); box = (kc, brows)
+static int encode_mat(CUtensorMap* m, const void* ptr, int64_t cols, int64_t rows, int kc, int brows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return SC_ERR_NO_DEVICE;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)brows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? SC_OK : SC_ERR_BAD_ARG;
+}
+
+extern "C" int sc_tc_supported(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return (major == 10 && get_encode() != nullptr) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights: OIHW f32 -> bf16 [Cout][tap][Cin] (optionally the flipped / transposed dgrad filter)
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ o, int Cout, int Cin,
+                                       int KK, int flip_t, int cin_pad, int cout_pad) {
+  // output logical shape [rows][KK][cols]: rows = Cout (or Cin when flip_t), cols = Cin (or Cout)
+  int rows = flip_t ? cin_pad : cout_pad, cols = flip_t ? cout_pad : cin_pad;
+  int64_t total = (int64_t)rows * KK * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % cols);
+    int64_t t = i / cols;
+    int tap = (int)(t % KK);
+    int r = (int)(t / KK);
+    float v = 0.f;
+    if (!flip_t) {
+      if (r < Cout && c < Cin) v = w[((int64_t)r * Cin + c) * KK + tap];
+    } else {
+      // dgrad: out channel r = ci, in channel c = co, tap mirrored
+      if (r < Cin && c < Cout) v = w[((int64_t)c * Cin + r) * KK + (KK - 1 - tap)];
+    }
+    o[i] = __float2bfloat16_rn(v);
+  }
+}
+
+extern "C" int sc_tc_pack_weights(const float* w_oihw, void* w_bf16, int Cout, int Cin, int KH, int KW,
+                                  int flip_transpose, int cin_pad, int cout_pad, void* stream) {
+  if (!w_oihw || !w_bf16 || cin_pad < Cin || cout_pad < Cout) return SC_ERR_BAD_ARG;
+  int64_t total = (int64_t)cin_pad * cout_pad * KH * KW;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  tc_pack_weights_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, (__nv_bfloat16*)w_bf16, Cout, Cin, KH * KW,
+                                                                   flip_transpose, cin_pad, cout_pad);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// fprop
+// ------------------------------------------------------------------------------------------------
+struct FpropParams {
+  int N, H, W, Cin, Cout, KH, KW;
+  int tiles_w, tiles_h;      // spatial patches per image
+  int m_tiles, n_tiles;
+  int block_n;               // multiple of 16, <= 256
+  int cchunks;               // Cin / KC
+  int stages;
+  int ldy;
+  __nv_bfloat16* y;
+  double* stats;             // optional [2][Cout] fp64 sum / sum of squares of the stored outputs
+};
+
+constexpr int kTcThreads = 192;
+
+template <int KC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, FpropParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int ROW_BYTES = KC * 2;
+  constexpr int A_BYTES = 128 * ROW_BYTES;
+  const int B_BYTES = p.block_n * ROW_BYTES;
+  const int STAGE_BYTES = (A_BYTES + B_BYTES + 1023) & ~1023;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);     // [2][block_n] per-CTA partial statistics
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int ksteps = p.KH * p.KW * p.cchunks;
+  const int pad = p.KH / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+        int tw = mt % p.tiles_w;
+        int t2 = mt / p.tiles_w;
+        int th = t2 % p.tiles_h;
+        int img = t2 / p.tiles_h;
+        int n0 = nt * p.block_n;
+        for (int tap = 0; tap < p.KH * p.KW; ++tap) {
+          int dy = tap / p.KW - pad, dx = tap % p.KW - pad;
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+            uint8_t* sB = sA + A_BYTES;
+            mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
+            tma_load_4d(sA, &tmA, cc * KC, tw * 16 + dx, th * 8 + dy, img, &full[stage]);
+            tma_load_2d(sB, &tmB, tap * p.Cin + cc * KC, n0, &full[stage]);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
+      constexpr uint32_t LAYOUT = layout_for_row_bytes(ROW_BYTES);
+      constexpr uint32_t SBO = 8 * ROW_BYTES;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          uint32_t aaddr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          uint32_t baddr = aaddr + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            uint64_t ad = make_smem_desc(aaddr + k * 32, 16, SBO, LAYOUT);
+            uint64_t bd = make_smem_desc(baddr + k * 32, 16, SBO, LAYOUT);
+            umma_bf16(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);
+      }
+    }
+  } else {
+    // epilogue: warp q reads TMEM lanes [32q, 32q+32)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;       // 0..127
+    if (p.stats)
+      for (int i = et; i < 2 * p.block_n; i += 128) s_stats[i] = 0.f;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
+      int tw = mt % p.tiles_w;
+      int t2 = mt / p.tiles_w;
+      int th = t2 % p.tiles_h;
+      int img = t2 / p.tiles_h;
+      int n0 = nt * p.block_n;
+      mbar_wait(&tfull[acc], (it >> 1) & 1);
+      tc_fence_after();
+      int h = th * 8 + row / 16, w = tw * 16 + row % 16;
+      __nv_bfloat16* yp = p.y + (((int64_t)img * p.H + h) * p.W + w) * p.ldy + n0;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (n0 + c0 < p.Cout) {
+          uint4 u0, u1;
+          __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&u0);
+          __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&u1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+          }
+          *reinterpret_cast<uint4*>(yp + c0) = u0;
+          *reinterpret_cast<uint4*>(yp + c0 + 8) = u1;
+          if (p.stats) {
+            // statistics of the STORED (bf16-rounded) values, reduced over the warp's 32 pixels
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float r = __bfloat162float(__float2bfloat16_rn(v[i]));
+              float s = warp_sum(r), s2 = warp_sum(r * r);
+              if (lane == 0) {
+                atomicAdd(&s_stats[c0 + i], s);
+                atomicAdd(&s_stats[p.block_n + c0 + i], s2);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (p.stats) {
+        // flush this tile's partial sums (fp64 global accumulators), then clear
+        asm volatile("bar.sync 1, 128;");
+        for (int i = et; i < p.block_n; i += 128) {
+          if (n0 + i < p.Cout) {
+            atomicAdd(&p.stats[n0 + i], (double)s_stats[i]);
+            atomicAdd(&p.stats[p.Cout + n0 + i], (double)s_stats[p.block_n + i]);
+          }
+          s_stats[i] = 0.f;
+          s_stats[p.block_n + i] = 0.f;
+        }
+        asm volatile("bar.sync 1, 128;");
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+static int pick_kc(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16); }
+
+extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void* y, int ldy, double* stats, int N,
+                                int H, int W, int Cin, int Cout, int KH, int KW, void* stream) {
+  if (!x || !w_bf16 || !y) return SC_ERR_BAD_ARG;
+  if (Cin % 16 || Cout % 16 || W % 16 || H % 8 || ldx % 8 || ldy % 8 || KH != KW || (KH != 1 && KH != 3))
+    return SC_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return SC_ERR_BAD_ARG;
+  const int kc = pick_kc(Cin);
+  FpropParams p;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW;
+  p.tiles_w = W / 16; p.tiles_h = H / 8;
+  p.m_tiles = N * p.tiles_w * p.tiles_h;
+  int nt = (Cout + 255) / 256;
+  p.block_n = ((Cout + nt - 1) / nt + 15) / 16 * 16;
+  p.n_tiles = (Cout + p.block_n - 1) / p.block_n;
+  p.cchunks = Cin / kc;
+  p.ldy = ldy; p.y = (__nv_bfloat16*)y; p.stats = stats;
+  const int stage_bytes = (128 * kc * 2 + p.block_n * kc * 2 + 1023) & ~1023;
+  const int tail = 1024 + 2 * 256 * 4 + 256;               // alignment slack + stats + barriers
+  int stages = (200 * 1024 - tail) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return SC_ERR_UNSUPPORTED;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + tail;
+
+  CUtensorMap tmA, tmB;
+  int rc = encode_act(&tmA, x, Cin, W, H, N, ldx, kc, 16, 8);
+  if (rc != SC_OK) return rc;
+  rc = encode_mat(&tmB, w_bf16, (int64_t)KH * KW * Cin, Cout, kc, p.block_n);
+  if (rc != SC_OK) return rc;
+  int total = p.m_tiles * p.n_tiles;
+  int grid = total < kNumSMs ? total : kNumSMs;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_FPROP(KC)                                                                                     \
+  do {                                                                                                       \
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_fprop_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem);                                                         \
+    if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                          \
+    tc_conv_fprop_kernel<KC><<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);                                   \
+  } while (0)
+  if (kc == 64) LAUNCH_FPROP(64);
+  else if (kc == 32) LAUNCH_FPROP(32);
+  else LAUNCH_FPROP(16);
+#undef LAUNCH_FPROP
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// wgrad
+// ------------------------------------------------------------------------------------------------
+struct WgradParams {
+  int N, H, W, Cin, Cout, KH, KW;
+  int tiles_w, tiles_h, p_tiles;   // 4 x 16 pixel patches
+  int m_blocks, n_blocks, ksplit;
+  int block_n, nb_boxes, kcb;      // dY tile: nb_boxes boxes of kcb channels
+  int cchunks, subs_total;         // sub-blocks (tap, channel chunk) of KC rows each
+  int stages;
+  float* dw;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int PIX = 64;                        // pixels (K) per stage: 4 rows x 16 cols
+  constexpr int SUBS = 128 / KC;                 // activation boxes per M block
+  constexpr int A_SUB_BYTES = PIX * KC * 2;
+  constexpr int A_BYTES = SUBS * A_SUB_BYTES;    // 16 KB
+  const int B_BOX_BYTES = PIX * p.kcb * 2;
+  const int B_BYTES = p.nb_boxes * B_BOX_BYTES;
+  const int STAGE_BYTES = (A_BYTES + B_BYTES + 1023) & ~1023;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item: (m block, n block, pixel split)
+  int wid = blockIdx.x;
+  const int mb = wid % p.m_blocks;
+  wid /= p.m_blocks;
+  const int nb = wid % p.n_blocks;
+  const int ks = wid / p.n_blocks;
+  const int n0 = nb * p.block_n;
+  const int per = (p.p_tiles + p.ksplit - 1) / p.ksplit;
+  const int t_begin = ks * per;
+  const int t_end = min(p.p_tiles, t_begin + per);
+  const int nsteps = max(0, t_end - t_begin);
+  int valid_subs = p.subs_total - mb * SUBS;
+  if (valid_subs > SUBS) valid_subs = SUBS;
+  const int pad = p.KH / 2;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        int tw = t % p.tiles_w;
+        int t2 = t / p.tiles_w;
+        int th = t2 % p.tiles_h;
+        int img = t2 / p.tiles_h;
+        mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+        uint8_t* sB = sA + A_BYTES;
+        mbar_arrive_expect_tx(&full[stage], valid_subs * A_SUB_BYTES + B_BYTES);
+        for (int s = 0; s < valid_subs; ++s) {
+          int j = mb * SUBS + s;
+          int tap = j / p.cchunks, cc = j - tap * p.cchunks;
+          int dy = tap / p.KW - pad, dx = tap % p.KW - pad;
+          tma_load_4d(sA + s * A_SUB_BYTES, &tmX, cc * KC, tw * 16 + dx, th * 4 + dy, img, &full[stage]);
+        }
+        for (int b = 0; b < p.nb_boxes; ++b)
+          tma_load_4d(sB + b * B_BOX_BYTES, &tmDY, n0 + b * p.kcb, tw * 16, th * 4, img, &full[stage]);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.block_n, 1, 1);
+      constexpr uint32_t A_LAYOUT = layout_for_row_bytes(KC * 2);
+      const uint32_t b_layout = layout_for_row_bytes(p.kcb * 2);
+      constexpr uint32_t A_SBO = 8 * KC * 2;
+      const uint32_t b_sbo = 8 * p.kcb * 2;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nsteps; ++i) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        uint32_t aaddr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+        uint32_t baddr = aaddr + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < PIX / 16; ++k) {
+          // K advances over pixels: 16 rows of (kc*2) bytes
+          uint64_t ad = make_smem_desc(aaddr + k * 16 * KC * 2, A_SUB_BYTES, A_SBO, A_LAYOUT);
+          uint64_t bd = make_smem_desc(baddr + k * 16 * p.kcb * 2, B_BOX_BYTES, b_sbo, b_layout);
+          umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == p.stages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(tfull);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    if (nsteps > 0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const int s = row / KC, cil = row % KC;
+      const int j = mb * SUBS + s;
+      const bool row_ok = s < valid_subs;
+      const int tap = row_ok ? j / p.cchunks : 0;
+      const int ci = row_ok ? (j - tap * p.cchunks) * KC + cil : 0;
+      const int KK = p.KH * p.KW;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            int co = n0 + c0 + i;
+            if (co < p.Cout) atomicAdd(&p.dw[((int64_t)co * p.Cin + ci) * KK + tap], v[i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, int N, int H, int W,
+                                int Cin, int Cout, int KH, int KW, void* stream) {
+  if (!x || !dy || !dw_oihw) return SC_ERR_BAD_ARG;
+  if (Cin % 16 || Cout % 16 || W % 16 || H % 4 || ldx % 8 || lddy % 8 || KH != KW || (KH != 1 && KH != 3))
+    return SC_ERR_UNSUPPORTED;
+  const int kc = pick_kc(Cin);
+  WgradParams p;
+  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW;
+  p.tiles_w = W / 16; p.tiles_h = H / 4;
+  p.p_tiles = N * p.tiles_w * p.tiles_h;
+  p.kcb = pick_kc(Cout);
+  int nt = (Cout + 255) / 256;
+  p.block_n = ((Cout + nt - 1) / nt + p.kcb - 1) / p.kcb * p.kcb;
+  if (p.block_n > 256) return SC_ERR_UNSUPPORTED;
+  p.n_blocks = (Cout + p.block_n - 1) / p.block_n;
+  p.nb_boxes = p.block_n / p.kcb;
+  p.cchunks = Cin / kc;
+  p.subs_total = KH * KW * p.cchunks;
+  const int subs = 128 / kc;
+  p.m_blocks = (p.subs_total + subs - 1) / subs;
+  int base = p.m_blocks * p.n_blocks;
+  int ksplit = (kNumSMs * 2 + base - 1) / base;
+  int max_split = (p.p_tiles + 7) / 8;                    // >= 8 pixel tiles (512 px) per CTA
+  if (ksplit > max_split) ksplit = max_split;
+  if (ksplit < 1) ksplit = 1;
+  p.ksplit = ksplit;
+  p.dw = dw_oihw;
+  const int stage_bytes = (64 * 128 * 2 + p.nb_boxes * 64 * p.kcb * 2 + 1023) & ~1023;
+  const int tail = 1024 + 256;
+  int stages = (200 * 1024 - tail) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return SC_ERR_UNSUPPORTED;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + tail;
+
+  CUtensorMap tmX, tmDY;
+  int rc = encode_act(&tmX, x, Cin, W, H, N, ldx, kc, 16, 4);
+  if (rc != SC_OK) return rc;
+  rc = encode_act(&tmDY, dy, Cout, W, H, N, lddy, p.kcb, 16, 4);
+  if (rc != SC_OK) return rc;
+  int grid = p.m_blocks * p.n_blocks * p.ksplit;
+  cudaStream_t st = (cudaStream_t)stream;
+#define LAUNCH_WGRAD(KC)                                                                                     \
+  do {                                                                                                       \
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem);                                                         \
+    if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                          \
+    tc_conv_wgrad_kernel<KC><<<grid, kTcThreads, smem, st>>>(tmX, tmDY, p);                                  \
+  } while (0)
+  if (kc == 64) LAUNCH_WGRAD(64);
+  else if (kc == 32) LAUNCH_WGRAD(32);
+  else LAUNCH_WGRAD(16);
+#undef LAUNCH_WGRAD
+  return check_launch();
+}

@@ -6,7 +6,3 @@ extern "C" int sc_mag1c_filter(const void*, int64_t, const void*, const uint8_t*
                                double, int, void*, void*) { return SC_ERR_UNSUPPORTED; }
 extern "C" int64_t sc_ratio_workspace_bytes(int, int64_t) { return -1; }
 extern "C" int sc_ratio_product(const float*, const float*, float*, int, int64_t, float, float, void*, void*) { return SC_ERR_UNSUPPORTED; }
-extern "C" int sc_tc_supported(void) { return 0; }
-extern "C" int sc_tc_pack_weights(const float*, void*, int, int, int, int, int, int, int, void*) { return SC_ERR_UNSUPPORTED; }
-extern "C" int sc_tc_conv_fprop(const void*, int, const void*, void*, int, double*, int, int, int, int, int, int, int, void*) { return SC_ERR_UNSUPPORTED; }
-extern "C" int sc_tc_conv_wgrad(const void*, int, const void*, int, float*, int, int, int, int, int, int, int, void*) { return SC_ERR_UNSUPPORTED; }

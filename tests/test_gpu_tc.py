@@ -1,0 +1,89 @@
+"""tcgen05 tensor-core convolution kernels (bf16 in, fp32 accumulate in TMEM) against PyTorch fp32
+on the same bf16-rounded operands."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from starcop_b200._lib import call, load  # noqa: E402
+
+DEV = "cuda"
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+CASES = [  # N, H, W, Cin, Cout, k
+    (1, 8, 16, 64, 64, 3),        # SW128, single tile
+    (2, 16, 32, 32, 32, 3),       # SW64
+    (2, 16, 16, 16, 16, 3),       # SW32 (decoder block 4 conv2 shape class)
+    (1, 8, 16, 96, 48, 3),        # Cin % 64 != 0 -> 32-channel chunks; N tile 48
+    (2, 8, 16, 128, 256, 1),      # pointwise
+    (1, 8, 16, 1376, 256, 3),     # decoder block 0 conv1 channel geometry
+    (1, 8, 16, 256, 1376, 3),     # its dgrad: 6 N tiles, ragged last tile
+    (3, 32, 32, 80, 32, 3),       # many tiles, 2 accumulator stages, persistent loop
+    (2, 16, 16, 320, 1280, 1),    # features.18
+]
+
+
+def make(N, H, W, Cin, Cout, k, seed=0):
+    torch.manual_seed(seed)
+    x = torch.randn(N, H, W, Cin, device=DEV).to(torch.bfloat16)
+    w = (torch.randn(Cout, Cin, k, k, device=DEV) / np.sqrt(Cin * k * k))
+    return x, w
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k", CASES)
+@pytest.mark.parametrize("with_stats", [False, True])
+def test_tc_fprop(N, H, W, Cin, Cout, k, with_stats):
+    assert load().sc_tc_supported() == 1
+    x, w = make(N, H, W, Cin, Cout, k)
+    wb = torch.empty(Cout * k * k * Cin, device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_pack_weights", w.data_ptr(), wb.data_ptr(), Cout, Cin, k, k, 0, Cin, Cout, st())
+    wq = wb.view(Cout, k, k, Cin).permute(0, 3, 1, 2).float()
+    assert torch.equal(wq, w.to(torch.bfloat16).float())
+    y = torch.full((N, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
+    call("sc_tc_conv_fprop", x.data_ptr(), Cin, wb.data_ptr(), y.data_ptr(), Cout, stats.data_ptr() if with_stats else 0,
+         N, H, W, Cin, Cout, k, k, st())
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wq, padding=k // 2).permute(0, 2, 3, 1)
+    err = (y.float() - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err
+    # bf16 rounding of an fp32-accumulated result: at most 1 bf16 ulp off the rounded reference
+    assert torch.allclose(y.float(), ref.to(torch.bfloat16).float(), rtol=1.6e-2, atol=1e-3)
+    if with_stats:
+        yf = y.double().reshape(-1, Cout)
+        assert torch.allclose(stats[:Cout], yf.sum(0), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(stats[Cout:], (yf * yf).sum(0), rtol=1e-4, atol=1e-2)
+
+
+def test_tc_dgrad_via_flipped_weights():
+    N, H, W, Cin, Cout, k = 2, 16, 16, 64, 32, 3
+    x, w = make(N, H, W, Cin, Cout, k)
+    dy = torch.randn(N, H, W, Cout, device=DEV).to(torch.bfloat16)
+    wt = torch.empty(Cin * k * k * Cout, device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_pack_weights", w.data_ptr(), wt.data_ptr(), Cout, Cin, k, k, 1, Cin, Cout, st())
+    dx = torch.empty(N, H, W, Cin, device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_conv_fprop", dy.data_ptr(), Cout, wt.data_ptr(), dx.data_ptr(), Cin, 0, N, H, W, Cout, Cin, k, k, st())
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.conv2d(xr, w.to(torch.bfloat16).float(), padding=1)
+    (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 3, 1, 2))
+    assert torch.allclose(dx.float(), gx.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k", CASES + [(16, 64, 64, 32, 16, 3), (4, 32, 32, 16, 16, 3)])
+def test_tc_wgrad(N, H, W, Cin, Cout, k):
+    x, w = make(N, H, W, Cin, Cout, k, seed=1)
+    dy = torch.randn(N, H, W, Cout, device=DEV).to(torch.bfloat16)
+    dw = torch.zeros(Cout, Cin, k, k, device=DEV)
+    call("sc_tc_conv_wgrad", x.data_ptr(), Cin, dy.data_ptr(), Cout, dw.data_ptr(), N, H, W, Cin, Cout, k, k, st())
+    torch.cuda.synchronize()
+    wr = w.clone().requires_grad_(True)
+    yr = F.conv2d(x.float().permute(0, 3, 1, 2), wr, padding=k // 2)
+    (gw,) = torch.autograd.grad(yr, wr, dy.float().permute(0, 3, 1, 2))
+    err = (dw - gw).abs().max().item()
+    assert err <= 2e-3 * gw.abs().max().item(), (err, gw.abs().max().item())
