@@ -73,18 +73,25 @@ int sc_dwconv_fprop(const void* x, int ldx, const float* scale, const float* shi
                     int dtype, void* stream);
 int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* dx, int lddx,
                     int N, int H, int W, int C, int stride, int dtype, void* stream);
+/* dw (C,1,3,3) += ...; workspace: sc_dwconv_wgrad_workspace_bytes(C) bytes of per-block partial rows */
+int64_t sc_dwconv_wgrad_workspace_bytes(int C);
 int sc_dwconv_wgrad(const void* x, int ldx, const float* scale, const float* shift, int act,
-                    const void* dy, int lddy, float* dw, int N, int H, int W, int C, int stride,
-                    int dtype, void* stream);
+                    const void* dy, int lddy, float* dw, float* workspace, int N, int H, int W, int C,
+                    int stride, int dtype, void* stream);
 
 /* training-mode BatchNorm2d (eps 1e-5, momentum 0.1 -- torchvision / smp defaults), split as
  * statistics -> finalize -> apply so that the normalise+activation runs in the consumer.
- * stats: sums[0..C) += sum_p y, sums[C..2C) += sum_p y*y   (fp64; caller zeroes) */
-int sc_bn_stats(const void* y, int ldy, double* sums, int64_t P, int C, int dtype, void* stream);
-/* training != 0: mean/var from sums over P pixels, running stats updated (unbiased var);
+ * Statistics are produced as ROWS OF PARTIAL SUMS (no global atomics, deterministic): a producer
+ * writes nrows <= SC_BN_MAX_PARTIALS rows of [sum(0..C) | sum of squares(C..2C)] fp64 into a buffer
+ * of sc_bn_partials_bytes(C) bytes and reports nrows through *nrows_host; the consumer sums them. */
+#define SC_BN_MAX_PARTIALS 296
+int64_t sc_bn_partials_bytes(int C);
+int sc_bn_stats(const void* y, int ldy, double* partials, int* nrows_host, int64_t P, int C, int dtype,
+                void* stream);
+/* training != 0: mean/var from the partial rows over P pixels, running stats updated (unbiased var);
  * training == 0: uses running_mean/var.  Emits scale = gamma*invstd, shift = beta - mean*scale,
  * and saves mean / invstd for the backward. */
-int sc_bn_finalize(const double* sums, int64_t P, int C, const float* gamma, const float* beta,
+int sc_bn_finalize(const double* partials, int nrows, int64_t P, int C, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, float momentum, float eps, int training,
                    float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
 /* z = act(y*scale+shift) (+ residual); written at channel stride ldz; upsample2 != 0 writes each
@@ -94,14 +101,16 @@ int sc_bn_act(const void* y, int ldy, const float* scale, const float* shift, in
               const void* residual, int ldr, void* z, int ldz, int N, int H, int W, int C,
               int upsample2, int dtype, void* stream);
 /* BN backward, phase 1: with g = dz * act'(y*scale+shift) (dz optionally 2x2 sum-pooled from a
- * (N,2H,2W,lddz) buffer when pooled != 0), red[0..C) += sum g, red[C..2C) += sum g*xhat (fp64). */
+ * (N,2H,2W,lddz) buffer when pooled != 0), partial rows of [sum g | sum g*xhat] (fp64, as above). */
 int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void* y, int ldy,
                      const float* scale, const float* shift, const float* mean, const float* invstd,
-                     int act, double* red, int N, int H, int W, int C, int dtype, void* stream);
-/* phase 2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dgamma += red[C..], dbeta += red[..C) */
+                     int act, double* partials, int* nrows_host, int N, int H, int W, int C, int dtype,
+                     void* stream);
+/* phase 2: dy = gamma*invstd*(g - mean(g) - xhat*mean(g*xhat)); dgamma += sum g*xhat, dbeta += sum g.
+ * Row [nrows] of `partials` receives the totals. */
 int sc_bn_bwd_apply(const void* dz, int lddz, int pooled, const void* y, int ldy,
                     const float* scale, const float* shift, const float* mean, const float* invstd,
-                    const float* gamma, int act, const double* red, void* dy, int lddy,
+                    const float* gamma, int act, double* partials, int nrows, void* dy, int lddy,
                     float* dgamma, float* dbeta, int N, int H, int W, int C, int dtype, void* stream);
 /* out (+)= a  [2x2 sum-pooled when pooled]; plain gradient routing for skip / residual fan-out */
 int sc_add_into(const void* a, int lda, int pooled, void* out, int ldo, int accumulate,
@@ -134,15 +143,19 @@ int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
                  float beta2, float eps, int step_host, float grad_scale, void* stream);
 
 /* ---- A8/A10: mag1c matched filter (starcop/models/mag1c.py:176-348) -------------------------
- * x: (G, P, ldx) BIP radiance rows, S window bands starting at x (caller offsets the pointer to
- * the first window band); template: S elements of `fp64 ? double : float`.
- * valid: optional (G,P) uint8 mask (func_by_groups, mag1c.py:161-172): groups with <= 10 valid
- * pixels are skipped and every non-valid pixel is written as -9999.
- * mf_out / albedo_out: (G,P) same float type.  workspace from sc_mag1c_workspace_bytes. */
-int64_t sc_mag1c_workspace_bytes(int G, int P, int S, int fp64);
-int sc_mag1c_filter(const void* x, int64_t ldx, const void* tmpl, const uint8_t* valid,
-                    void* mf_out, void* albedo_out, int G, int P, int S, int num_iter, double alpha,
-                    int fp64, void* workspace, void* stream);
+ * One pixel group per CTA (a detector column of a tile, process_aviris.py:211-212, or any pixel set
+ * func_by_groups builds, mag1c.py:161-172).  x: radiance, band s of pixel `pix` at
+ * x[pix*pixel_stride + s] for the S window bands (the caller offsets x to the first window band);
+ * element type float (AVIRIS, process_aviris.py:199) or double (EMIT, mag1c_emit.py:46) per `fp64`.
+ * pix_idx: (G, pmax) int32 pixel indices of each group, counts: G valid lengths (NULL = all pmax).
+ * Groups with <= 10 pixels are skipped (mag1c.py:166): their outputs keep the caller's pre-fill
+ * (-9999).  tmpl: S doubles.  mf_out / albedo_out: per-pixel outputs indexed by `pix` (scatter).
+ * num_iter = 0 is the plain matched filter `rmf`; alpha = diagonal loading (mag1c.py:246).
+ * status: optional device int, incremented per group whose covariance was not positive definite. */
+int64_t sc_mag1c_smem_bytes(int S);
+int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_t* pix_idx, const int32_t* counts,
+                    int pmax, const double* tmpl, void* mf_out, void* albedo_out, int G, int S,
+                    int num_iter, double alpha, int fp64, int* status, void* stream);
 
 /* ---- A11/A13: band ratio product (starcop/data/feature_extration.py:32-56) ------------------
  * per tile: exact 5/95 percentiles (np.percentile linear) of each band by radix select, inlier
@@ -159,15 +172,22 @@ int sc_threshold_opening(const float* pred, float threshold, int64_t* out, uint8
 /* ---- tcgen05 tensor-core path (bf16 storage, fp32 accumulate in TMEM) -----------------------
  * Implicit-GEMM convolution: A = activation tile fetched by TMA (shifted box per filter tap, zero
  * fill = padding), B = packed bf16 weights [Cout][KH*KW][Cin], accumulators in TMEM.
- * Supported: stride 1, KH=KW in {1,3}, Cin % 16 == 0, Cout % 16 == 0, W % 16 == 0 or H*W % 128 == 0.
- * Optional epilogue: per-channel sum / sum-of-squares of the stored outputs into `stats` (fp64). */
+ * Supported: stride 1, KH=KW in {1,3}, Cin % 8 == 0, Cout % 8 == 0, W % 16 == 0, H % 8 == 0
+ * (anything else returns SC_ERR_UNSUPPORTED and the caller uses the fp32-FMA kernels).
+ * Packed weights: bf16 [cout_pad][tap][cin_pad] with cin_pad = Cin rounded up to the channel chunk
+ * (64 if Cin%64==0, 32 if Cin%32==0, else 16) -- sc_tc_cin_pad(Cin).
+ * stride 2 (the encoder stem) samples the input through the tensor map's element strides.
+ * Optional epilogue: per-channel sum / sum-of-squares of the stored outputs as BatchNorm partial
+ * rows (`stats` + *stats_rows_host, see sc_bn_stats); accumulate != 0 adds onto the existing y. */
+int sc_tc_cin_pad(int Cin);
 int sc_tc_supported(void);
 int sc_tc_pack_weights(const float* w_oihw, void* w_bf16, int Cout, int Cin, int KH, int KW,
                        int flip_transpose, int cin_pad, int cout_pad, void* stream);
 int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void* y, int ldy, double* stats,
-                     int N, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
+                     int* stats_rows_host, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                     int stride, int accumulate, void* stream);
 int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw,
-                     int N, int H, int W, int Cin, int Cout, int KH, int KW, void* stream);
+                     int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, void* stream);
 
 #ifdef __cplusplus
 }

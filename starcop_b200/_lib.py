@@ -24,29 +24,32 @@ SIGNATURES = {
     "sc_pack_weights": [P, P, I, I, I, I, I, P],
     "sc_dwconv_fprop": [P, I, P, P, I, P, P, I, I, I, I, I, I, I, P],
     "sc_dwconv_dgrad": [P, I, P, P, I, I, I, I, I, I, I, P],
-    "sc_dwconv_wgrad": [P, I, P, P, I, P, I, P, I, I, I, I, I, I, P],
-    "sc_bn_stats": [P, I, P, L, I, I, P],
-    "sc_bn_finalize": [P, L, I, P, P, P, P, F, F, I, P, P, P, P, P],
+    "sc_dwconv_wgrad_workspace_bytes": [I],
+    "sc_dwconv_wgrad": [P, I, P, P, I, P, I, P, P, I, I, I, I, I, I, P],
+    "sc_bn_partials_bytes": [I],
+    "sc_bn_stats": [P, I, P, P, L, I, I, P],
+    "sc_bn_finalize": [P, I, L, I, P, P, P, P, F, F, I, P, P, P, P, P],
     "sc_bn_act": [P, I, P, P, I, P, I, P, I, I, I, I, I, I, I, P],
-    "sc_bn_bwd_reduce": [P, I, I, P, I, P, P, P, P, I, P, I, I, I, I, I, P],
-    "sc_bn_bwd_apply": [P, I, I, P, I, P, P, P, P, P, I, P, P, I, P, P, I, I, I, I, I, P],
+    "sc_bn_bwd_reduce": [P, I, I, P, I, P, P, P, P, I, P, P, I, I, I, I, I, P],
+    "sc_bn_bwd_apply": [P, I, I, P, I, P, P, P, P, P, I, P, I, P, I, P, P, I, I, I, I, I, P],
     "sc_add_into": [P, I, I, P, I, I, I, I, I, I, I, P],
     "sc_head_fprop": [P, I, P, P, P, I, I, I, I, I, P],
     "sc_head_bwd": [P, I, P, P, P, I, P, P, I, I, I, I, I, P],
     "sc_bce_fused": [P, P, P, F, I, L, F, P, P, P, P, P, P, P, P, P, P, P, P],
     "sc_adam_step": [P, P, P, P, L, F, F, F, F, I, F, P],
-    "sc_mag1c_workspace_bytes": [I, I, I, I],
-    "sc_mag1c_filter": [P, L, P, P, P, P, I, I, I, I, D, I, P, P],
+    "sc_mag1c_smem_bytes": [I],
+    "sc_mag1c_filter": [P, L, P, P, I, P, P, P, I, I, I, D, I, P, P],
     "sc_ratio_workspace_bytes": [I, L],
     "sc_ratio_product": [P, P, P, I, L, F, F, P, P],
     "sc_weight_mag1c": [P, P, L, P],
     "sc_threshold_opening": [P, F, P, P, I, I, I, P],
     "sc_tc_supported": [],
     "sc_tc_pack_weights": [P, P, I, I, I, I, I, I, I, P],
-    "sc_tc_conv_fprop": [P, I, P, P, I, P, I, I, I, I, I, I, I, P],
-    "sc_tc_conv_wgrad": [P, I, P, I, P, I, I, I, I, I, I, I, P],
+    "sc_tc_cin_pad": [I],
+    "sc_tc_conv_fprop": [P, I, P, P, I, P, P, I, I, I, I, I, I, I, I, I, P],
+    "sc_tc_conv_wgrad": [P, I, P, I, P, I, I, I, I, I, I, I, I, P],
 }
-_RESTYPES = {"sc_last_cuda_error": ctypes.c_char_p, "sc_mag1c_workspace_bytes": c_int64,
+_RESTYPES = {"sc_last_cuda_error": ctypes.c_char_p, "sc_mag1c_smem_bytes": c_int64, "sc_bn_partials_bytes": c_int64, "sc_dwconv_wgrad_workspace_bytes": c_int64,
              "sc_ratio_workspace_bytes": c_int64}
 
 _lib = None

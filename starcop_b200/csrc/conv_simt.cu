@@ -304,7 +304,9 @@ extern "C" int sc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// depthwise 3x3 (pad 1, stride 1|2), optional BN+act of the producer applied on load
+// depthwise 3x3 (pad 1, stride 1|2), optional BN+act of the producer applied on load.
+// Bandwidth-bound: 8-channel vectors, weights staged once per block in shared memory as [tap][C]
+// (the torch layout [C][9] would cost 72 strided scalar loads per output vector).
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ f8 load_bnact(const T* p, const f8& sc_, const f8& sh, bool has_bn, int act) {
@@ -316,13 +318,24 @@ __device__ __forceinline__ f8 load_bnact(const T* p, const f8& sc_, const f8& sh
   return v;
 }
 
+__device__ __forceinline__ void stage_dw_weights(float* ws, const float* __restrict__ w, int C) {
+  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
+    int c = i / 9, tap = i - c * 9;
+    ws[tap * C + c] = w[i];
+  }
+  __syncthreads();
+}
+
 template <typename T>
-__global__ void dwconv_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, int act, const float* __restrict__ w,
-                                    T* __restrict__ y, int ldy, int N, int H, int W, int C, int stride, int Ho,
-                                    int Wo) {
+__global__ void __launch_bounds__(256)
+dwconv_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
+                    const float* __restrict__ shift, int act, const float* __restrict__ w,
+                    T* __restrict__ y, int ldy, int N, int H, int W, int C, int stride, int Ho, int Wo) {
+  extern __shared__ float ws[];   // [9][C]
+  stage_dw_weights(ws, w, C);
   int CV = C / 8;
   int64_t total = (int64_t)N * Ho * Wo * CV;
+  const bool has_bn = scale != nullptr;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int cv = (int)(idx % CV);
@@ -332,7 +345,6 @@ __global__ void dwconv_fprop_kernel(const T* __restrict__ x, int ldx, const floa
     int ho = (int)(t % Ho);
     int n = (int)(t / Ho);
     f8 sc_, sh;
-    bool has_bn = scale != nullptr;
     if (has_bn) {
       sc_ = load8<float>(scale + cv * 8);
       sh = load8<float>(shift + cv * 8);
@@ -349,8 +361,9 @@ __global__ void dwconv_fprop_kernel(const T* __restrict__ x, int ldx, const floa
         int iw = wo * stride - 1 + kw;
         if (iw < 0 || iw >= W) continue;
         f8 v = load_bnact<T>(x + (((int64_t)n * H + ih) * W + iw) * ldx + cv * 8, sc_, sh, has_bn, act);
+        f8 wv = load8<float>(ws + (kh * 3 + kw) * C + cv * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v.v[i], w[(cv * 8 + i) * 9 + kh * 3 + kw], acc[i]);
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v.v[i], wv.v[i], acc[i]);
       }
     }
     f8 o;
@@ -362,26 +375,29 @@ __global__ void dwconv_fprop_kernel(const T* __restrict__ x, int ldx, const floa
 
 static int ew_blocks2(int64_t total) {
   int64_t b = (total + 255) / 256;
-  int64_t cap = (int64_t)kNumSMs * 16;
+  int64_t cap = (int64_t)kNumSMs * 8;
   return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
 }
 
 extern "C" int sc_dwconv_fprop(const void* x, int ldx, const float* scale, const float* shift, int act,
                                const float* w, void* y, int ldy, int N, int H, int W, int C, int stride, int dtype,
                                void* stream) {
-  if (!x || !w || !y || C % 8 || ldx % 8 || ldy % 8 || (stride != 1 && stride != 2)) return SC_ERR_BAD_ARG;
+  if (!x || !w || !y || C % 8 || ldx % 8 || ldy % 8 || (stride != 1 && stride != 2) || C > 1280) return SC_ERR_BAD_ARG;
   int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   int64_t total = (int64_t)N * Ho * Wo * (C / 8);
-  SC_DISPATCH_DTYPE(dtype, (dwconv_fprop_kernel<T><<<ew_blocks2(total), 256, 0, (cudaStream_t)stream>>>(
+  size_t smem = (size_t)9 * C * sizeof(float);
+  SC_DISPATCH_DTYPE(dtype, (dwconv_fprop_kernel<T><<<ew_blocks2(total), 256, smem, (cudaStream_t)stream>>>(
                                (const T*)x, ldx, scale, shift, act, w, (T*)y, ldy, N, H, W, C, stride, Ho, Wo)));
   return check_launch();
 }
 
 // dx[n,ih,iw,c] = sum_{kh,kw : (ih+1-kh) % s == 0 ...} dy[n,(ih+1-kh)/s,(iw+1-kw)/s,c] * w[c,kh,kw]
 template <typename T>
-__global__ void dwconv_dgrad_kernel(const T* __restrict__ dy, int lddy, const float* __restrict__ w,
-                                    T* __restrict__ dx, int lddx, int N, int H, int W, int C, int stride, int Ho,
-                                    int Wo) {
+__global__ void __launch_bounds__(256)
+dwconv_dgrad_kernel(const T* __restrict__ dy, int lddy, const float* __restrict__ w,
+                    T* __restrict__ dx, int lddx, int N, int H, int W, int C, int stride, int Ho, int Wo) {
+  extern __shared__ float ws[];
+  stage_dw_weights(ws, w, C);
   int CV = C / 8;
   int64_t total = (int64_t)N * H * W * CV;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -408,8 +424,9 @@ __global__ void dwconv_dgrad_kernel(const T* __restrict__ dy, int lddy, const fl
         int wo = tw / stride;
         if (wo >= Wo) continue;
         f8 g = load8<T>(dy + (((int64_t)n * Ho + ho) * Wo + wo) * lddy + cv * 8);
+        f8 wv = load8<float>(ws + (kh * 3 + kw) * C + cv * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(g.v[i], w[(cv * 8 + i) * 9 + kh * 3 + kw], acc[i]);
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(g.v[i], wv.v[i], acc[i]);
       }
     }
     f8 o;
@@ -421,19 +438,23 @@ __global__ void dwconv_dgrad_kernel(const T* __restrict__ dy, int lddy, const fl
 
 extern "C" int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* dx, int lddx, int N, int H, int W,
                                int C, int stride, int dtype, void* stream) {
-  if (!dy || !w || !dx || C % 8 || lddy % 8 || lddx % 8 || (stride != 1 && stride != 2)) return SC_ERR_BAD_ARG;
+  if (!dy || !w || !dx || C % 8 || lddy % 8 || lddx % 8 || (stride != 1 && stride != 2) || C > 1280) return SC_ERR_BAD_ARG;
   int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   int64_t total = (int64_t)N * H * W * (C / 8);
-  SC_DISPATCH_DTYPE(dtype, (dwconv_dgrad_kernel<T><<<ew_blocks2(total), 256, 0, (cudaStream_t)stream>>>(
+  size_t smem = (size_t)9 * C * sizeof(float);
+  SC_DISPATCH_DTYPE(dtype, (dwconv_dgrad_kernel<T><<<ew_blocks2(total), 256, smem, (cudaStream_t)stream>>>(
                                (const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C, stride, Ho, Wo)));
   return check_launch();
 }
 
+// wgrad: thread = (pixel lane, 8-channel vector), 72 fp32 partials per thread; each block writes ONE
+// row of partial sums [C][9] to the workspace, a second tiny kernel adds the rows into dw.
 template <typename T>
-__global__ void dwconv_wgrad_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, int act, const T* __restrict__ dy, int lddy,
-                                    float* __restrict__ dw, int N, int H, int W, int C, int stride, int Ho, int Wo,
-                                    int CVB, int PL) {
+__global__ void __launch_bounds__(256)
+dwconv_wgrad_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
+                    const float* __restrict__ shift, int act, const T* __restrict__ dy, int lddy,
+                    float* __restrict__ partial, int N, int H, int W, int C, int stride, int Ho, int Wo,
+                    int CVB, int PL) {
   extern __shared__ float smf[];   // [CVB*8][9]
   int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
   int cv = blockIdx.y * CVB + cvl;
@@ -478,16 +499,36 @@ __global__ void dwconv_wgrad_kernel(const T* __restrict__ x, int ldx, const floa
       for (int i = 0; i < 8; ++i) atomicAdd(&smf[(cvl * 8 + i) * 9 + tp], acc[tp][i]);
   }
   __syncthreads();
+  float* row = partial + (int64_t)blockIdx.x * C * 9;
   for (int i = threadIdx.x; i < CVB * 72; i += blockDim.x) {
     int c = blockIdx.y * CVB * 8 + i / 9;
-    if (c < C) atomicAdd(&dw[c * 9 + i % 9], smf[i]);
+    if (c < C) row[c * 9 + i % 9] = smf[i];
   }
 }
 
+__global__ void dwconv_wgrad_sum_kernel(const float* __restrict__ partial, int nrows, int n, float* __restrict__ dw) {
+  __shared__ float sh[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (i < n)
+    for (int r = ty; r < nrows; r += 8) s += partial[(int64_t)r * n + i];
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || i >= n) return;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) s += sh[j][tx];
+  dw[i] += s;
+}
+
+constexpr int kDwMaxRows = 296;
+extern "C" int64_t sc_dwconv_wgrad_workspace_bytes(int C) { return (int64_t)kDwMaxRows * C * 9 * sizeof(float); }
+
 extern "C" int sc_dwconv_wgrad(const void* x, int ldx, const float* scale, const float* shift, int act,
-                               const void* dy, int lddy, float* dw, int N, int H, int W, int C, int stride,
-                               int dtype, void* stream) {
-  if (!x || !dy || !dw || C % 8 || ldx % 8 || lddy % 8 || (stride != 1 && stride != 2)) return SC_ERR_BAD_ARG;
+                               const void* dy, int lddy, float* dw, float* workspace, int N, int H, int W, int C,
+                               int stride, int dtype, void* stream) {
+  if (!x || !dy || !dw || !workspace || C % 8 || ldx % 8 || lddy % 8 || (stride != 1 && stride != 2))
+    return SC_ERR_BAD_ARG;
   int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   int CV = C / 8;
   int CVB = CV < 64 ? CV : 64;      // 64*72 floats = 18 KB smem
@@ -495,13 +536,16 @@ extern "C" int sc_dwconv_wgrad(const void* x, int ldx, const float* scale, const
   int gy = (CV + CVB - 1) / CVB;
   int64_t P = (int64_t)N * Ho * Wo;
   int64_t want = (P + PL * 8 - 1) / (PL * 8);
-  int64_t cap = (kNumSMs * 8) / gy;
+  int64_t cap = (kNumSMs * 4) / gy;
   if (cap < 1) cap = 1;
+  if (cap > kDwMaxRows) cap = kDwMaxRows;
   int bx = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
   dim3 grid(bx, gy);
   size_t smem = (size_t)CVB * 72 * sizeof(float);
-  SC_DISPATCH_DTYPE(dtype, (dwconv_wgrad_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
-                               (const T*)x, ldx, scale, shift, act, (const T*)dy, lddy, dw, N, H, W, C, stride, Ho,
+  cudaStream_t st = (cudaStream_t)stream;
+  SC_DISPATCH_DTYPE(dtype, (dwconv_wgrad_kernel<T><<<grid, 256, smem, st>>>(
+                               (const T*)x, ldx, scale, shift, act, (const T*)dy, lddy, workspace, N, H, W, C, stride, Ho,
                                Wo, CVB, PL)));
+  dwconv_wgrad_sum_kernel<<<(C * 9 + 31) / 32, dim3(32, 8), 0, st>>>(workspace, bx, C * 9, dw);
   return check_launch();
 }

@@ -43,13 +43,15 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
 }
 
 // NHWC bf16 activation tensor (C, W, H, N) with channel stride ld; box = (kc, bw, bh, 1)
-static int encode_act(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int ld, int kc, int bw, int bh) {
+// es > 1: the box samples every es-th pixel (strided convolution); TMA copies ceil(box/es) elements
+static int encode_act(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int ld, int kc, int bw, int bh,
+                      int es_ = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return SC_ERR_NO_DEVICE;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(bw * es_), (cuuint32_t)(bh * es_), 1};
+  cuuint32_t es[4] = {1, (cuuint32_t)es_, (cuuint32_t)es_, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -116,13 +118,16 @@ extern "C" int sc_tc_pack_weights(const float* w_oihw, void* w_bf16, int Cout, i
 // fprop
 // ------------------------------------------------------------------------------------------------
 struct FpropParams {
-  int N, H, W, Cin, Cout, KH, KW;
+  int N, H, W, Cin, Cout, KH, KW;   // H, W: OUTPUT spatial size
+  int stride;
   int tiles_w, tiles_h;      // spatial patches per image
   int m_tiles, n_tiles;
   int block_n;               // multiple of 16, <= 256
-  int cchunks;               // Cin / KC
+  int cchunks;               // ceil(Cin / KC)
+  int groups;                // (tap, channel chunk) K groups per pipeline stage
   int stages;
   int ldy;
+  int accumulate;            // y += result (gradient fan-in)
   __nv_bfloat16* y;
   double* stats;             // optional [2][Cout] fp64 sum / sum of squares of the stored outputs
 };
@@ -136,14 +141,15 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int ROW_BYTES = KC * 2;
   constexpr int A_BYTES = 128 * ROW_BYTES;
-  const int B_BYTES = p.block_n * ROW_BYTES;
-  const int STAGE_BYTES = (A_BYTES + B_BYTES + 1023) & ~1023;
+  const int B_BYTES = (p.block_n * ROW_BYTES + 1023) & ~1023;
+  const int G = p.groups;
+  const int STAGE_BYTES = G * (A_BYTES + B_BYTES);       // [G x A][G x B], every box 1024-aligned
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);     // [2][block_n] per-CTA partial statistics
+  float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);     // [2][Cout] per-CTA partial statistics
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -167,6 +173,7 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int ksteps = p.KH * p.KW * p.cchunks;
+  const int nstages_per_tile = (ksteps + G - 1) / G;
   const int pad = p.KH / 2;
 
   if (warp == 0) {
@@ -180,19 +187,23 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int th = t2 % p.tiles_h;
         int img = t2 / p.tiles_h;
         int n0 = nt * p.block_n;
-        for (int tap = 0; tap < p.KH * p.KW; ++tap) {
-          int dy = tap / p.KW - pad, dx = tap % p.KW - pad;
-          for (int cc = 0; cc < p.cchunks; ++cc) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
-            uint8_t* sB = sA + A_BYTES;
-            mbar_arrive_expect_tx(&full[stage], A_BYTES + B_BYTES);
-            tma_load_4d(sA, &tmA, cc * KC, tw * 16 + dx, th * 8 + dy, img, &full[stage]);
-            tma_load_2d(sB, &tmB, tap * p.Cin + cc * KC, n0, &full[stage]);
-            if (++stage == p.stages) {
-              stage = 0;
-              phase ^= 1;
-            }
+        for (int s0 = 0; s0 < ksteps; s0 += G) {
+          const int g_here = min(G, ksteps - s0);
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+          uint8_t* sB = sA + G * A_BYTES;
+          mbar_arrive_expect_tx(&full[stage], g_here * (A_BYTES + p.block_n * ROW_BYTES));
+          for (int g = 0; g < g_here; ++g) {
+            int ks = s0 + g;
+            int tap = ks / p.cchunks, cc = ks - tap * p.cchunks;
+            int dy = tap / p.KW - pad, dx = tap % p.KW - pad;
+            tma_load_4d(sA + g * A_BYTES, &tmA, cc * KC, (tw * 16) * p.stride + dx, (th * 8) * p.stride + dy, img,
+                        &full[stage]);
+            tma_load_2d(sB + g * B_BYTES, &tmB, ks * KC, n0, &full[stage]);
+          }
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
           }
         }
       }
@@ -210,16 +221,19 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int ks = 0; ks < ksteps; ++ks) {
+        for (int si = 0; si < nstages_per_tile; ++si) {
+          const int g_here = min(G, ksteps - si * G);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           uint32_t aaddr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          uint32_t baddr = aaddr + A_BYTES;
+          uint32_t baddr = aaddr + G * A_BYTES;
+          for (int g = 0; g < g_here; ++g) {
 #pragma unroll
-          for (int k = 0; k < KC / 16; ++k) {
-            uint64_t ad = make_smem_desc(aaddr + k * 32, 16, SBO, LAYOUT);
-            uint64_t bd = make_smem_desc(baddr + k * 32, 16, SBO, LAYOUT);
-            umma_bf16(d_tmem, ad, bd, idesc, (ks > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < KC / 16; ++k) {
+              uint64_t ad = make_smem_desc(aaddr + g * A_BYTES + k * 32, 16, SBO, LAYOUT);
+              uint64_t bd = make_smem_desc(baddr + g * B_BYTES + k * 32, 16, SBO, LAYOUT);
+              umma_bf16(d_tmem, ad, bd, idesc, (si > 0 || g > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty[stage]);
           if (++stage == p.stages) {
@@ -235,8 +249,12 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;       // 0..127
-    if (p.stats)
-      for (int i = et; i < 2 * p.block_n; i += 128) s_stats[i] = 0.f;
+    if (p.stats) {
+      for (int i = et; i < 2 * p.Cout; i += 128) s_stats[i] = 0.f;
+      asm volatile("bar.sync 1, 128;");
+    }
+    // after the recursive-halving reduction below, this lane owns column (lane >> 1) of each 16-column group
+    const int my_col = lane >> 1;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -254,46 +272,75 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);
-        if (n0 + c0 < p.Cout) {
-          uint4 u0, u1;
-          __nv_bfloat162* h0 = reinterpret_cast<__nv_bfloat162*>(&u0);
-          __nv_bfloat162* h1 = reinterpret_cast<__nv_bfloat162*>(&u1);
+        // channels are handled in 8-wide halves (Cout % 8 == 0; a ragged last N tile is masked)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            h0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-            h1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+        for (int hf = 0; hf < 2; ++hf) {
+          float* vv = v + hf * 8;
+          if (n0 + c0 + hf * 8 >= p.Cout) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) vv[i] = 0.f;
+            continue;
           }
-          *reinterpret_cast<uint4*>(yp + c0) = u0;
-          *reinterpret_cast<uint4*>(yp + c0 + 8) = u1;
-          if (p.stats) {
-            // statistics of the STORED (bf16-rounded) values, reduced over the warp's 32 pixels
+          uint4 u;
+          __nv_bfloat162* hh = reinterpret_cast<__nv_bfloat162*>(&u);
+          if (p.accumulate) {
+            uint4 o = *reinterpret_cast<const uint4*>(yp + c0 + hf * 8);
+            const __nv_bfloat162* oh = reinterpret_cast<const __nv_bfloat162*>(&o);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              float r = __bfloat162float(__float2bfloat16_rn(v[i]));
-              float s = warp_sum(r), s2 = warp_sum(r * r);
-              if (lane == 0) {
-                atomicAdd(&s_stats[c0 + i], s);
-                atomicAdd(&s_stats[p.block_n + c0 + i], s2);
-              }
+            for (int i = 0; i < 4; ++i) {
+              float2 f = __bfloat1622float2(oh[i]);
+              vv[2 * i] += f.x;
+              vv[2 * i + 1] += f.y;
             }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) hh[i] = __floats2bfloat162_rn(vv[2 * i], vv[2 * i + 1]);
+          *reinterpret_cast<uint4*>(yp + c0 + hf * 8) = u;
+          if (p.stats) {
+            // statistics are taken of the STORED (bf16-rounded) values
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2 f = __bfloat1622float2(hh[i]);
+              vv[2 * i] = f.x;
+              vv[2 * i + 1] = f.y;
+            }
+          }
+        }
+        if (p.stats) {
+          // column sums over the warp's 32 pixel rows by recursive halving: 16+16 shuffles per 16 columns
+          float sq[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
+#pragma unroll
+          for (int wdt = 8, mask = 16; wdt >= 1; wdt >>= 1, mask >>= 1) {
+            const bool upper = (lane & mask) != 0;
+#pragma unroll
+            for (int i = 0; i < wdt; ++i) {
+              float send = upper ? v[i] : v[i + wdt];
+              float keep = upper ? v[i + wdt] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+              float send2 = upper ? sq[i] : sq[i + wdt];
+              float keep2 = upper ? sq[i + wdt] : sq[i];
+              sq[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, mask);
+            }
+          }
+          float s1 = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+          float s2 = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
+          int ch = n0 + c0 + my_col;
+          if ((lane & 1) == 0 && ch < p.Cout) {
+            atomicAdd(&s_stats[ch], s1);
+            atomicAdd(&s_stats[p.Cout + ch], s2);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
-      if (p.stats) {
-        // flush this tile's partial sums (fp64 global accumulators), then clear
-        asm volatile("bar.sync 1, 128;");
-        for (int i = et; i < p.block_n; i += 128) {
-          if (n0 + i < p.Cout) {
-            atomicAdd(&p.stats[n0 + i], (double)s_stats[i]);
-            atomicAdd(&p.stats[p.Cout + n0 + i], (double)s_stats[p.block_n + i]);
-          }
-          s_stats[i] = 0.f;
-          s_stats[p.block_n + i] = 0.f;
-        }
-        asm volatile("bar.sync 1, 128;");
-      }
+    }
+    if (p.stats) {
+      // one partial row per CTA (BatchNorm partial-sum protocol, see sc_bn_stats): no global atomics
+      asm volatile("bar.sync 1, 128;");
+      double* rowp = p.stats + (int64_t)blockIdx.x * 2 * p.Cout;
+      for (int i = et; i < 2 * p.Cout; i += 128) rowp[i] = (double)s_stats[i];
     }
   }
   tc_fence_before();
@@ -305,25 +352,44 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 static int pick_kc(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16); }
+extern "C" int sc_tc_cin_pad(int Cin) {
+  int kc = pick_kc(Cin);
+  return (Cin + kc - 1) / kc * kc;
+}
 
-extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void* y, int ldy, double* stats, int N,
-                                int H, int W, int Cin, int Cout, int KH, int KW, void* stream) {
-  if (!x || !w_bf16 || !y) return SC_ERR_BAD_ARG;
-  if (Cin % 16 || Cout % 16 || W % 16 || H % 8 || ldx % 8 || ldy % 8 || KH != KW || (KH != 1 && KH != 3))
+extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void* y, int ldy, double* stats,
+                                int* stats_rows_host, int N, int H, int W, int Cin, int Cout, int KH, int KW,
+                                int stride, int accumulate, void* stream) {
+  if (!x || !w_bf16 || !y || (stats && !stats_rows_host)) return SC_ERR_BAD_ARG;
+  if (stride != 1 && stride != 2) return SC_ERR_UNSUPPORTED;
+  const int Ho = stride == 1 ? H : (H + 2 * (KH / 2) - KH) / 2 + 1;
+  const int Wo = stride == 1 ? W : (W + 2 * (KW / 2) - KW) / 2 + 1;
+  if (Cin < 1 || Cout % 8 || Wo % 16 || Ho % 8 || ldx % 8 || ldy % 8 || KH != KW || (KH != 1 && KH != 3))
     return SC_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15)) return SC_ERR_BAD_ARG;
   const int kc = pick_kc(Cin);
   FpropParams p;
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW;
-  p.tiles_w = W / 16; p.tiles_h = H / 8;
+  p.N = N; p.H = Ho; p.W = Wo; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.stride = stride;
+  p.tiles_w = Wo / 16; p.tiles_h = Ho / 8;
   p.m_tiles = N * p.tiles_w * p.tiles_h;
   int nt = (Cout + 255) / 256;
   p.block_n = ((Cout + nt - 1) / nt + 15) / 16 * 16;
   p.n_tiles = (Cout + p.block_n - 1) / p.block_n;
-  p.cchunks = Cin / kc;
-  p.ldy = ldy; p.y = (__nv_bfloat16*)y; p.stats = stats;
-  const int stage_bytes = (128 * kc * 2 + p.block_n * kc * 2 + 1023) & ~1023;
-  const int tail = 1024 + 2 * 256 * 4 + 256;               // alignment slack + stats + barriers
+  p.cchunks = (Cin + kc - 1) / kc;      // a ragged last chunk is zero-filled by TMA (and by the weight pack)
+  p.ldy = ldy; p.y = (__nv_bfloat16*)y; p.stats = stats; p.accumulate = accumulate;
+  const int ksteps = KH * KW * p.cchunks;
+  const int group_bytes = 128 * kc * 2 + ((p.block_n * kc * 2 + 1023) & ~1023);
+  // thin layers issue only a few MMA cycles per (tap, chunk) group: put several groups in one
+  // pipeline stage so the MMA thread pays one barrier round trip per >= ~256 tensor-pipe cycles
+  const int group_cycles = (kc / 16) * (p.block_n / 2);
+  int groups = (256 + group_cycles - 1) / group_cycles;
+  if (groups > ksteps) groups = ksteps;
+  if (groups > 9) groups = 9;
+  while (groups > 1 && groups * group_bytes > 64 * 1024) --groups;
+  if (groups < 1) groups = 1;
+  p.groups = groups;
+  const int stage_bytes = groups * group_bytes;
+  const int tail = 1024 + 256 + (stats ? 2 * Cout * 4 : 0);   // alignment slack + barriers + statistics
   int stages = (200 * 1024 - tail) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return SC_ERR_UNSUPPORTED;
@@ -331,12 +397,13 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
   const size_t smem = (size_t)stages * stage_bytes + tail;
 
   CUtensorMap tmA, tmB;
-  int rc = encode_act(&tmA, x, Cin, W, H, N, ldx, kc, 16, 8);
+  int rc = encode_act(&tmA, x, Cin, W, H, N, ldx, kc, 16, 8, stride);
   if (rc != SC_OK) return rc;
-  rc = encode_mat(&tmB, w_bf16, (int64_t)KH * KW * Cin, Cout, kc, p.block_n);
+  rc = encode_mat(&tmB, w_bf16, (int64_t)KH * KW * p.cchunks * kc, Cout, kc, p.block_n);
   if (rc != SC_OK) return rc;
   int total = p.m_tiles * p.n_tiles;
   int grid = total < kNumSMs ? total : kNumSMs;
+  if (stats) *stats_rows_host = grid;
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FPROP(KC)                                                                                     \
   do {                                                                                                       \
@@ -356,7 +423,8 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
 // wgrad
 // ------------------------------------------------------------------------------------------------
 struct WgradParams {
-  int N, H, W, Cin, Cout, KH, KW;
+  int N, H, W, Cin, Cout, KH, KW;   // H, W: OUTPUT (dY) spatial size
+  int stride;
   int tiles_w, tiles_h, p_tiles;   // 4 x 16 pixel patches
   int m_blocks, n_blocks, ksplit;
   int block_n, nb_boxes, kcb;      // dY tile: nb_boxes boxes of kcb channels
@@ -431,7 +499,8 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
           int j = mb * SUBS + s;
           int tap = j / p.cchunks, cc = j - tap * p.cchunks;
           int dy = tap / p.KW - pad, dx = tap % p.KW - pad;
-          tma_load_4d(sA + s * A_SUB_BYTES, &tmX, cc * KC, tw * 16 + dx, th * 4 + dy, img, &full[stage]);
+          tma_load_4d(sA + s * A_SUB_BYTES, &tmX, cc * KC, (tw * 16) * p.stride + dx, (th * 4) * p.stride + dy, img,
+                      &full[stage]);
         }
         for (int b = 0; b < p.nb_boxes; ++b)
           tma_load_4d(sB + b * B_BOX_BYTES, &tmDY, n0 + b * p.kcb, tw * 16, th * 4, img, &full[stage]);
@@ -478,9 +547,10 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       tc_fence_after();
       const int s = row / KC, cil = row % KC;
       const int j = mb * SUBS + s;
-      const bool row_ok = s < valid_subs;
+      bool row_ok = s < valid_subs;
       const int tap = row_ok ? j / p.cchunks : 0;
       const int ci = row_ok ? (j - tap * p.cchunks) * KC + cil : 0;
+      row_ok = row_ok && ci < p.Cin;
       const int KK = p.KH * p.KW;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
@@ -505,14 +575,17 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
 }
 
 extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, int N, int H, int W,
-                                int Cin, int Cout, int KH, int KW, void* stream) {
+                                int Cin, int Cout, int KH, int KW, int stride, void* stream) {
   if (!x || !dy || !dw_oihw) return SC_ERR_BAD_ARG;
-  if (Cin % 16 || Cout % 16 || W % 16 || H % 4 || ldx % 8 || lddy % 8 || KH != KW || (KH != 1 && KH != 3))
+  if (stride != 1 && stride != 2) return SC_ERR_UNSUPPORTED;
+  const int Ho = stride == 1 ? H : (H + 2 * (KH / 2) - KH) / 2 + 1;
+  const int Wo = stride == 1 ? W : (W + 2 * (KW / 2) - KW) / 2 + 1;
+  if (Cin < 1 || Cout % 8 || Wo % 16 || Ho % 4 || ldx % 8 || lddy % 8 || KH != KW || (KH != 1 && KH != 3))
     return SC_ERR_UNSUPPORTED;
   const int kc = pick_kc(Cin);
   WgradParams p;
-  p.N = N; p.H = H; p.W = W; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW;
-  p.tiles_w = W / 16; p.tiles_h = H / 4;
+  p.N = N; p.H = Ho; p.W = Wo; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.stride = stride;
+  p.tiles_w = Wo / 16; p.tiles_h = Ho / 4;
   p.p_tiles = N * p.tiles_w * p.tiles_h;
   p.kcb = pick_kc(Cout);
   int nt = (Cout + 255) / 256;
@@ -520,7 +593,7 @@ extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy
   if (p.block_n > 256) return SC_ERR_UNSUPPORTED;
   p.n_blocks = (Cout + p.block_n - 1) / p.block_n;
   p.nb_boxes = p.block_n / p.kcb;
-  p.cchunks = Cin / kc;
+  p.cchunks = (Cin + kc - 1) / kc;
   p.subs_total = KH * KW * p.cchunks;
   const int subs = 128 / kc;
   p.m_blocks = (p.subs_total + subs - 1) / subs;
@@ -540,9 +613,9 @@ extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy
   const size_t smem = (size_t)stages * stage_bytes + tail;
 
   CUtensorMap tmX, tmDY;
-  int rc = encode_act(&tmX, x, Cin, W, H, N, ldx, kc, 16, 4);
+  int rc = encode_act(&tmX, x, Cin, W, H, N, ldx, kc, 16, 4, stride);
   if (rc != SC_OK) return rc;
-  rc = encode_act(&tmDY, dy, Cout, W, H, N, lddy, p.kcb, 16, 4);
+  rc = encode_act(&tmDY, dy, Cout, Wo, Ho, N, lddy, p.kcb, 16, 4);
   if (rc != SC_OK) return rc;
   int grid = p.m_blocks * p.n_blocks * p.ksplit;
   cudaStream_t st = (cudaStream_t)stream;

@@ -74,13 +74,17 @@ static RedGeom red_geom(int C) {
 }
 static int red_blocks(int64_t P, int PL, int gy) {
   int64_t want = (P + PL * 8 - 1) / (PL * 8);   // >= 8 pixels per thread
-  int64_t cap = (kNumSMs * 8) / gy;
+  int64_t cap = (kNumSMs * 4) / gy;
   if (cap < 1) cap = 1;
+  if (cap > SC_BN_MAX_PARTIALS) cap = SC_BN_MAX_PARTIALS;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 
+// Block (x, y) reduces its pixel slice for channel group y and writes ONE row of partial sums:
+// partials[x][0..C) = sum, partials[x][C..2C) = sum of squares.  No global atomics (thousands of
+// fp64 atomics on a few hundred addresses serialise in L2), and the result is deterministic.
 template <typename T>
-__global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __restrict__ sums, int64_t P,
+__global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __restrict__ partials, int64_t P,
                                 int C, int CVB, int PL) {
   extern __shared__ double sm[];   // [2][CVB*8]
   int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
@@ -107,36 +111,59 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __rest
     }
   }
   __syncthreads();
+  double* row = partials + (int64_t)blockIdx.x * 2 * C;
   for (int i = threadIdx.x; i < CVB * 8; i += blockDim.x) {
     int c = blockIdx.y * CVB * 8 + i;
     if (c < C) {
-      atomicAdd(&sums[c], sm[i]);
-      atomicAdd(&sums[C + c], sm[CVB * 8 + i]);
+      row[c] = sm[i];
+      row[C + c] = sm[CVB * 8 + i];
     }
   }
 }
 
-extern "C" int sc_bn_stats(const void* y, int ldy, double* sums, int64_t P, int C, int dtype, void* stream) {
-  if (!y || !sums || C % 8 || ldy % 8 || P <= 0) return SC_ERR_BAD_ARG;
+extern "C" int64_t sc_bn_partials_bytes(int C) { return (int64_t)(SC_BN_MAX_PARTIALS + 1) * 2 * C * sizeof(double); }
+
+extern "C" int sc_bn_stats(const void* y, int ldy, double* partials, int* nrows_host, int64_t P, int C, int dtype,
+                           void* stream) {
+  if (!y || !partials || !nrows_host || C % 8 || ldy % 8 || P <= 0) return SC_ERR_BAD_ARG;
   RedGeom g = red_geom(C);
   dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
+  *nrows_host = (int)grid.x;
   size_t smem = 2 * g.CVB * 8 * sizeof(double);
   SC_DISPATCH_DTYPE(dtype, (bn_stats_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
-                               (const T*)y, ldy, sums, P, C, g.CVB, g.PL)));
+                               (const T*)y, ldy, partials, P, C, g.CVB, g.PL)));
   return check_launch();
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t P, int C,
+// block = 32 channels x 8 row slices: the nrows partial rows are summed 8-way in parallel
+__global__ void bn_finalize_kernel(const double* __restrict__ partials, int nrows, int64_t P, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, float momentum, float eps,
                                    int training, float* scale, float* shift, float* save_mean,
                                    float* save_invstd) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double sh[2][8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  double s1 = 0.0, s2 = 0.0;
+  if (training && c < C) {
+    for (int r = ty; r < nrows; r += 8) {
+      s1 += partials[(int64_t)r * 2 * C + c];
+      s2 += partials[(int64_t)r * 2 * C + C + c];
+    }
+  }
+  sh[0][ty][tx] = s1;
+  sh[1][ty][tx] = s2;
+  __syncthreads();
+  if (ty != 0 || c >= C) return;
   float mean, invstd;
   if (training) {
-    double m = sums[c] / (double)P;
-    double var = sums[C + c] / (double)P - m * m;   // biased, used for normalisation
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      s1 += sh[0][j][tx];
+      s2 += sh[1][j][tx];
+    }
+    double m = s1 / (double)P;
+    double var = s2 / (double)P - m * m;   // biased, used for normalisation
     if (var < 0.0) var = 0.0;
     mean = (float)m;
     invstd = (float)(1.0 / sqrt(var + (double)eps));
@@ -157,14 +184,14 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int64_t P, i
   if (save_invstd) save_invstd[c] = invstd;
 }
 
-extern "C" int sc_bn_finalize(const double* sums, int64_t P, int C, const float* gamma, const float* beta,
+extern "C" int sc_bn_finalize(const double* sums, int nrows, int64_t P, int C, const float* gamma, const float* beta,
                               float* running_mean, float* running_var, float momentum, float eps,
                               int training, float* scale, float* shift, float* save_mean,
                               float* save_invstd, void* stream) {
   if (C <= 0 || !scale || !shift || (training && !sums) || (!training && (!running_mean || !running_var)))
     return SC_ERR_BAD_ARG;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
-      sums, P, C, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift,
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      sums, nrows, P, C, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift,
       save_mean, save_invstd);
   return check_launch();
 }
@@ -247,7 +274,7 @@ template <typename T>
 __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int pooled, const T* __restrict__ y,
                                      int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, int act,
-                                     double* __restrict__ red, int64_t P, int C, int H, int W, int CVB, int PL) {
+                                     double* __restrict__ partials, int64_t P, int C, int H, int W, int CVB, int PL) {
   extern __shared__ double sm[];
   int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
   int cv = blockIdx.y * CVB + cvl;
@@ -277,23 +304,25 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int poo
     }
   }
   __syncthreads();
+  double* row = partials + (int64_t)blockIdx.x * 2 * C;
   for (int i = threadIdx.x; i < CVB * 8; i += blockDim.x) {
     int c = blockIdx.y * CVB * 8 + i;
     if (c < C) {
-      atomicAdd(&red[c], sm[i]);
-      atomicAdd(&red[C + c], sm[CVB * 8 + i]);
+      row[c] = sm[i];
+      row[C + c] = sm[CVB * 8 + i];
     }
   }
 }
 
 extern "C" int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void* y, int ldy,
                                 const float* scale, const float* shift, const float* mean,
-                                const float* invstd, int act, double* red, int N, int H, int W, int C,
-                                int dtype, void* stream) {
-  if (!dz || !y || !red || C % 8 || ldy % 8 || lddz % 8) return SC_ERR_BAD_ARG;
+                                const float* invstd, int act, double* red, int* nrows_host, int N, int H, int W,
+                                int C, int dtype, void* stream) {
+  if (!dz || !y || !red || !nrows_host || C % 8 || ldy % 8 || lddz % 8) return SC_ERR_BAD_ARG;
   int64_t P = (int64_t)N * H * W;
   RedGeom g = red_geom(C);
   dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
+  *nrows_host = (int)grid.x;
   size_t smem = 2 * g.CVB * 8 * sizeof(double);
   SC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
                                (const T*)dz, lddz, pooled, (const T*)y, ldy, scale, shift, mean, invstd, act,
@@ -308,12 +337,6 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dz, int lddz, int pool
                                     const float* __restrict__ gamma, int act, const double* __restrict__ red,
                                     T* __restrict__ dy, int lddy, float* dgamma, float* dbeta, int64_t total,
                                     int CV, int C, int H, int W, double invP) {
-  if (blockIdx.x == 0 && dgamma) {   // parameter gradients: dbeta = sum g, dgamma = sum g*xhat
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dbeta[c] += (float)red[c];
-      dgamma[c] += (float)red[C + c];
-    }
-  }
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int cv = (int)(idx % CV);
@@ -336,15 +359,39 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dz, int lddz, int pool
   }
 }
 
+// totals row = sum of the partial rows; also the parameter gradients dbeta = sum g, dgamma = sum g*xhat
+__global__ void bn_bwd_totals_kernel(double* __restrict__ partials, int nrows, int C, float* dgamma, float* dbeta) {
+  __shared__ double sh[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * 32 + tx;
+  double s = 0.0;
+  if (i < 2 * C)
+    for (int r = ty; r < nrows; r += 8) s += partials[(int64_t)r * 2 * C + i];
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || i >= 2 * C) return;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) s += sh[j][tx];
+  partials[(int64_t)nrows * 2 * C + i] = s;
+  if (dgamma) {
+    if (i < C) dbeta[i] += (float)s;
+    else dgamma[i - C] += (float)s;
+  }
+}
+
 extern "C" int sc_bn_bwd_apply(const void* dz, int lddz, int pooled, const void* y, int ldy,
                                const float* scale, const float* shift, const float* mean,
-                               const float* invstd, const float* gamma, int act, const double* red,
+                               const float* invstd, const float* gamma, int act, double* partials, int nrows,
                                void* dy, int lddy, float* dgamma, float* dbeta, int N, int H, int W, int C,
                                int dtype, void* stream) {
-  if (!dz || !y || !red || !dy || C % 8 || ldy % 8 || lddz % 8 || lddy % 8) return SC_ERR_BAD_ARG;
+  if (!dz || !y || !partials || !dy || nrows < 1 || nrows > SC_BN_MAX_PARTIALS || C % 8 || ldy % 8 || lddz % 8 ||
+      lddy % 8)
+    return SC_ERR_BAD_ARG;
   (void)gamma;
   int CV = C / 8;
   int64_t P = (int64_t)N * H * W, total = P * CV;
+  bn_bwd_totals_kernel<<<(2 * C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(partials, nrows, C, dgamma, dbeta);
+  const double* red = partials + (int64_t)nrows * 2 * C;
   SC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
                                (const T*)dz, lddz, pooled, (const T*)y, ldy, scale, shift, mean, invstd, gamma,
                                act, red, (T*)dy, lddy, dgamma, dbeta, total, CV, C, H, W, 1.0 / (double)P)));
@@ -506,11 +553,22 @@ __global__ void head_wgrad_kernel(const T* __restrict__ x, int ldx, const float*
         }
       }
     }
+  }
+  // lanes with equal (lane % CV) own the same channels (32 % CV == 0): butterfly over the others
+  const int lane = threadIdx.x & 31;
+  for (int m = CV; m < 32; m <<= 1) {
 #pragma unroll
     for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&sm[tp * C + cv * 8 + i], acc[tp][i]);
-    if (cv == 0) atomicAdd(&sm[9 * C], bsum);
+      for (int i = 0; i < 8; ++i) acc[tp][i] += __shfl_xor_sync(0xffffffffu, acc[tp][i], m);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, m);
+  }
+  if (lane < CV) {
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(&sm[tp * C + lane * 8 + i], acc[tp][i]);
+    if (lane == 0) atomicAdd(&sm[9 * C], bsum);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
@@ -522,7 +580,7 @@ __global__ void head_wgrad_kernel(const T* __restrict__ x, int ldx, const float*
 
 extern "C" int sc_head_bwd(const void* x, int ldx, const float* w, const float* dlogits, void* dx, int lddx,
                            float* dw, float* dbias, int N, int H, int W, int C, int dtype, void* stream) {
-  if (!x || !w || !dlogits || C % 8 || C > kHeadMaxC || ldx % 8) return SC_ERR_BAD_ARG;
+  if (!x || !w || !dlogits || C % 8 || C > kHeadMaxC || ldx % 8 || 32 % (C / 8)) return SC_ERR_BAD_ARG;
   int64_t total = (int64_t)N * H * W;
   cudaStream_t st = (cudaStream_t)stream;
   if (dx) {

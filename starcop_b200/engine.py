@@ -7,6 +7,8 @@ statistics/finalize/apply so the normalise+activation runs fused in the consumer
 nearest-x2 upsample + concat fused into the producer's store, skip features written once straight
 into the decoder's concat buffers, gradients routed through channel-slice views instead of copies.
 """
+import ctypes
+
 import torch
 
 from . import _lib
@@ -92,6 +94,7 @@ class UNetEngine:
         self.tape = []
         self.record = False
         self.stream = 0
+        self.use_tc = self.dtype == SC_BF16 and bool(_lib.load().sc_tc_supported())
 
     # ------------------------------------------------------------------ memory
     def begin_step(self):
@@ -141,14 +144,22 @@ class UNetEngine:
             call("sc_add_into", g.ptr, g.ld, 0, x.grad.ptr, x.grad.ld, 1, x.N, x.H, x.W, x.C, self.dtype, self.stream)
 
     # ------------------------------------------------------------------ primitive layers
-    def _bn_forward(self, y, bn, training):
+    def _partials(self, C):
+        """buffer for BatchNorm partial-sum rows (written, never accumulated: no zeroing needed)"""
+        return self.arena.alloc(_lib.load().sc_bn_partials_bytes(C))
+
+    def _bn_forward(self, y, bn, training, sums=None):
+        """sums: (partials ptr, nrows) already produced by the conv's epilogue (tcgen05 path)."""
         C, P = y.C, y.pixels
-        sums = self.f32buf(2 * C, zero=training, double=True) if training else 0
         scale, shift = self.f32buf(C), self.f32buf(C)
         mean, invstd = self.f32buf(C), self.f32buf(C)
-        if training:
-            call("sc_bn_stats", y.ptr, y.ld, sums, P, C, self.dtype, self.stream)
-        call("sc_bn_finalize", sums, P, C, self.p[bn + ".weight"].data_ptr(), self.p[bn + ".bias"].data_ptr(),
+        if training and sums is None:
+            part, n = self._partials(C), ctypes.c_int(0)
+            call("sc_bn_stats", y.ptr, y.ld, part, ctypes.byref(n), P, C, self.dtype, self.stream)
+            sums = (part, n.value)
+        part, nrows = sums if training else (0, 0)
+        call("sc_bn_finalize", part, nrows, P, C, self.p[bn + ".weight"].data_ptr(),
+             self.p[bn + ".bias"].data_ptr(),
              self.b[bn + ".running_mean"].data_ptr(), self.b[bn + ".running_var"].data_ptr(),
              BN_MOMENTUM, BN_EPS, int(training), scale, shift, mean, invstd, self.stream)
         return scale, shift, mean, invstd
@@ -169,47 +180,74 @@ class UNetEngine:
         else:
             dz, pooled = z.grad, 0
         assert dz is not None, f"no gradient reached BN {bn}"
-        red = self.f32buf(2 * C, zero=True, double=True)
+        red, n = self._partials(C), ctypes.c_int(0)
         call("sc_bn_bwd_reduce", dz.ptr, dz.ld, pooled, y.ptr, y.ld, scale, shift, mean, invstd, act, red,
-             y.N, y.H, y.W, C, self.dtype, self.stream)
+             ctypes.byref(n), y.N, y.H, y.W, C, self.dtype, self.stream)
         dy = self.new_like(y)
         call("sc_bn_bwd_apply", dz.ptr, dz.ld, pooled, y.ptr, y.ld, scale, shift, mean, invstd,
-             self.p[bn + ".weight"].data_ptr(), act, red, dy.ptr, dy.ld,
+             self.p[bn + ".weight"].data_ptr(), act, red, n.value, dy.ptr, dy.ld,
              self.g[bn + ".weight"].data_ptr(), self.g[bn + ".bias"].data_ptr(),
              y.N, y.H, y.W, C, self.dtype, self.stream)
         return dy
 
-    def _dense_fprop(self, x, wname, k, stride, bias=None):
+    def _tc_ok(self, x, cin, cout, k, stride):
+        """tcgen05 path: bf16 storage, stride 1, 8-aligned channels, spatial patch 8 x 16."""
+        ho, wo = (x.H - 1) // stride + 1, (x.W - 1) // stride + 1
+        return (self.dtype == SC_BF16 and self.use_tc and (stride == 1 or (stride == 2 and k == 3)) and k in (1, 3)
+                and cout % 8 == 0 and wo % 16 == 0 and ho % 8 == 0 and x.ld % 8 == 0)
+
+    def _dense_fprop(self, x, wname, k, stride, want_stats=False):
+        """-> (y, sums): sums is the fp64 [2*Cout] statistics buffer when the conv epilogue produced it."""
         w = self.p[wname]
         cout, cin = w.shape[0], w.shape[1]
         assert cin == x.C, (wname, cin, x.C)
         pad = k // 2
-        wp = self.f32buf(w.numel())
-        call("sc_pack_weights", w.data_ptr(), wp, cout, cin, k, k, 0, self.stream)
         Ho, Wo = (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1
         y = self.new(x.N, Ho, Wo, cout)
+        if self._tc_ok(x, cin, cout, k, stride):
+            cpad = _lib.load().sc_tc_cin_pad(cin)
+            wb = self.arena.alloc(cout * k * k * cpad * 2)
+            call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, k, k, 0, cpad, cout, self.stream)
+            part, n = (self._partials(cout), ctypes.c_int(0)) if want_stats else (0, ctypes.c_int(0))
+            call("sc_tc_conv_fprop", x.ptr, x.ld, wb, y.ptr, y.ld, part, ctypes.byref(n), x.N, x.H, x.W, cin, cout,
+                 k, k, stride, 0, self.stream)
+            return y, ((part, n.value) if want_stats else None)
+        wp = self.f32buf(w.numel())
+        call("sc_pack_weights", w.data_ptr(), wp, cout, cin, k, k, 0, self.stream)
         call("sc_conv_fprop", x.ptr, x.ld, wp, 0, y.ptr, y.ld, x.N, x.H, x.W, cin, cout, k, k, stride, pad,
              self.dtype, 0, self.stream)
-        return y
+        return y, None
 
     def _dense_backward(self, x, dy, wname, k, stride, need_dx=True):
         w = self.p[wname]
         cout, cin = w.shape[0], w.shape[1]
         pad = k // 2
-        call("sc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), x.N, x.H, x.W, cin, cout,
-             k, k, stride, pad, self.dtype, self.stream)
+        tc = self._tc_ok(x, cin, cout, k, stride) and dy.ld % 8 == 0
+        if tc:
+            call("sc_tc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), x.N, x.H, x.W, cin, cout,
+                 k, k, stride, self.stream)
+        else:
+            call("sc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), x.N, x.H, x.W, cin, cout,
+                 k, k, stride, pad, self.dtype, self.stream)
         if need_dx:
             assert stride == 1
-            wp = self.f32buf(w.numel())
-            call("sc_pack_weights", w.data_ptr(), wp, cout, cin, k, k, 1, self.stream)
             dst, acc = self._grad_dst(x)
-            call("sc_conv_fprop", dy.ptr, dy.ld, wp, 0, dst.ptr, dst.ld, dy.N, dy.H, dy.W, cout, cin, k, k, 1, pad,
-                 self.dtype, acc, self.stream)
+            if tc:
+                cpad = _lib.load().sc_tc_cin_pad(cout)          # dgrad conv: input channels = Cout
+                wb = self.arena.alloc(cin * k * k * cpad * 2)
+                call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, k, k, 1, cin, cpad, self.stream)
+                call("sc_tc_conv_fprop", dy.ptr, dy.ld, wb, dst.ptr, dst.ld, 0, 0, dy.N, dy.H, dy.W, cout, cin, k, k,
+                     1, acc, self.stream)
+            else:
+                wp = self.f32buf(w.numel())
+                call("sc_pack_weights", w.data_ptr(), wp, cout, cin, k, k, 1, self.stream)
+                call("sc_conv_fprop", dy.ptr, dy.ld, wp, 0, dst.ptr, dst.ld, dy.N, dy.H, dy.W, cout, cin, k, k, 1, pad,
+                     self.dtype, acc, self.stream)
 
     # ------------------------------------------------------------------ composite blocks
     def conv_bn_act(self, x, wname, bn, k, stride, act, training, out=None, up2=False, residual=None, need_dx=True):
-        y = self._dense_fprop(x, wname, k, stride)
-        stats = self._bn_forward(y, bn, training)
+        y, sums = self._dense_fprop(x, wname, k, stride, want_stats=training)
+        stats = self._bn_forward(y, bn, training, sums)
         z = self._bn_act(y, stats[0], stats[1], act, out=out, up2=up2, residual=residual)
         if self.record:
             def bwd():
@@ -224,9 +262,9 @@ class UNetEngine:
         use_res = stride == 1 and cin == cout
         i = 0
         if t != 1:
-            y1 = self._dense_fprop(x, f"{prefix}.conv.0.0.weight", 1, 1)
+            y1, sums1 = self._dense_fprop(x, f"{prefix}.conv.0.0.weight", 1, 1, want_stats=training)
             bn1 = f"{prefix}.conv.0.1"
-            st1 = self._bn_forward(y1, bn1, training)
+            st1 = self._bn_forward(y1, bn1, training, sums1)
             dw_in, dw_scale, dw_shift, dw_act = y1, st1[0], st1[1], ACT_RELU6
             i = 1
         else:
@@ -240,16 +278,17 @@ class UNetEngine:
         st2 = self._bn_forward(y2, bn2, training)
         z2 = self._bn_act(y2, st2[0], st2[1], ACT_RELU6)
         wpr, bn3 = f"{prefix}.conv.{i + 1}.weight", f"{prefix}.conv.{i + 2}"
-        y3 = self._dense_fprop(z2, wpr, 1, 1)
-        st3 = self._bn_forward(y3, bn3, training)
+        y3, sums3 = self._dense_fprop(z2, wpr, 1, 1, want_stats=training)
+        st3 = self._bn_forward(y3, bn3, training, sums3)
         z3 = self._bn_act(y3, st3[0], st3[1], ACT_NONE, out=out, residual=x if use_res else None)
         if self.record:
             def bwd():
                 dy3 = self._bn_backward(z3, y3, bn3, st3, ACT_NONE, False)
                 self._dense_backward(z2, dy3, wpr, 1, 1)
                 dy2 = self._bn_backward(z2, y2, bn2, st2, ACT_RELU6, False)
+                ws = self.arena.alloc(_lib.load().sc_dwconv_wgrad_workspace_bytes(hidden))
                 call("sc_dwconv_wgrad", dw_in.ptr, dw_in.ld, dw_scale, dw_shift, dw_act, dy2.ptr, dy2.ld,
-                     self.g[wdw].data_ptr(), x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
+                     self.g[wdw].data_ptr(), ws, x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
                 if use_res:
                     self._alias_grad(x, z3.grad)        # d(x + f(x)) -> x gets dz3 as is
                 if t != 1:

@@ -1,0 +1,134 @@
+"""Drop-in for the hot functions of ``starcop/models/mag1c.py`` on the CUDA matched-filter kernel
+(``sc_mag1c_filter``): ``acrwl1mf`` (:176-280), ``rmf`` (:283-348), ``func_by_groups`` (:116-174),
+``get_mask_bad_bands`` (:98-113), plus the tile driver used by ``run_mag1c``
+(starcop/process_aviris.py:183-219: BIP cube, contiguous band slice, groups = detector columns).
+
+Template generation (``generate_template_from_bands``, a one-off host computation over the
+31800-sample CH4 look-up table) stays on the host and is passed in as an array.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+
+NODATA = -9999
+SCALING = 1e5
+EPSILON = 1e-9
+
+
+def get_mask_bad_bands(wave):
+    """mag1c.py:98-113: keep 400..2485 nm minus the 1350-1420 / 1800-1945 nm water bands."""
+    wave = np.asarray(wave)
+    return ~(((wave < 400) | (wave > 2485)) | (((wave > 1350) & (wave < 1420)) | ((wave > 1800) & (wave < 1945))))
+
+
+def band_keep_aviris(wavelengths):
+    """process_aviris.py:192-206: the matched-filter window as ONE contiguous slice."""
+    wavelengths = np.asarray(wavelengths)
+    keep = get_mask_bad_bands(wavelengths) & (wavelengths > 2122) & (wavelengths < 2488)
+    idx = np.where(keep)[0]
+    if not len(idx) or np.any(np.diff(idx) != 1):
+        raise AssertionError("Selected bands are not contiguous")
+    return slice(int(idx[0]), int(idx[-1]) + 1)
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _filter(x_flat, pixel_stride, pix_idx, counts, template, mf_out, al_out, S, num_iter, alpha):
+    dev = x_flat.device
+    fp64 = x_flat.dtype == torch.float64
+    tmpl = torch.as_tensor(np.asarray(template, dtype=np.float64) if not torch.is_tensor(template)
+                           else template.detach().double().cpu().numpy()).to(dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    G, pmax = pix_idx.shape
+    _lib.call("sc_mag1c_filter", x_flat.data_ptr(), pixel_stride, pix_idx.data_ptr(),
+              counts.data_ptr() if counts is not None else 0, pmax, tmpl.data_ptr(), mf_out.data_ptr(),
+              al_out.data_ptr(), G, S, num_iter, float(alpha), int(fp64), status.data_ptr(), _stream(dev))
+    return status
+
+
+@torch.no_grad()
+def acrwl1mf(x, template, num_iter=30, alpha=0., check=True):
+    """x: [b, p, s] CUDA tensor (float32 or float64) -> (mf [b,p,1] in ppm*m, albedo R [b,p,1])."""
+    if not x.is_cuda:
+        raise _lib.StarcopB200Error("starcop_b200 runs on CUDA tensors only (no CPU path)")
+    assert x.dim() == 3, "x must be [batch(groups), pixels, spectrum]"
+    x = x.contiguous()
+    b, p, s = x.shape
+    idx = torch.arange(b * p, dtype=torch.int32, device=x.device).view(b, p)
+    mf = torch.empty(b, p, 1, dtype=x.dtype, device=x.device)
+    al = torch.empty_like(mf)
+    status = _filter(x, s, idx, None, template, mf, al, s, num_iter, alpha)
+    if check and int(status.item()):
+        # the reference raises from torch.linalg.cholesky in the same situation
+        raise torch.linalg.LinAlgError(f"linalg.cholesky: covariance of {int(status.item())} group(s) is not positive-definite")
+    return mf, al
+
+
+@torch.no_grad()
+def rmf(x, template, alpha=0., check=True):
+    """mag1c.py:283-348 with the default flags: the plain (albedo-normalised) matched filter."""
+    return acrwl1mf(x, template, num_iter=0, alpha=alpha, check=check)
+
+
+@torch.no_grad()
+def func_by_groups(x, groups, template, mask=None, num_iter=30, alpha=0.):
+    """mag1c.py:116-174 for func = acrwl1mf: x (H, W, S) CUDA radiance, groups (H, W) integer map,
+    mask (H, W) valid pixels -> (mf, albedo), each (H, W), NODATA where not computed.
+    The gather lists are built on the host like the reference's loops; ALL groups then run in one launch."""
+    H, W, S = x.shape
+    dev = x.device
+    g = np.asarray(groups.cpu() if torch.is_tensor(groups) else groups)
+    if mask is None:
+        m = torch.all(x > NODATA, dim=-1).cpu().numpy()
+    else:
+        m = np.asarray(mask.cpu() if torch.is_tensor(mask) else mask).astype(bool)
+    flat = np.arange(H * W, dtype=np.int32).reshape(H, W)
+    ids = np.sort(np.unique(g[m]))
+    lists = [flat[(g == i) & m] for i in ids]
+    pmax = max((len(l) for l in lists), default=1)
+    idx = np.zeros((max(len(lists), 1), pmax), dtype=np.int32)
+    cnt = np.zeros(max(len(lists), 1), dtype=np.int32)
+    for k, l in enumerate(lists):
+        idx[k, :len(l)] = l
+        cnt[k] = len(l)
+    mf = torch.full((H, W), float(NODATA), dtype=x.dtype, device=dev)
+    al = torch.full((H, W), float(NODATA), dtype=x.dtype, device=dev)
+    if len(lists):
+        xc = x.contiguous()
+        _filter(xc, S, torch.from_numpy(idx).to(dev), torch.from_numpy(cnt).to(dev), template, mf, al, S, num_iter, alpha)
+    return mf, al
+
+
+_IDX_CACHE = {}
+
+
+def _column_groups(n, H, W, dev):
+    """pixel lists for groups = image columns of n stacked (H, W) tiles: group (t, w) = pixels (t, :, w)."""
+    key = (n, H, W, str(dev))
+    if key not in _IDX_CACHE:
+        t = torch.arange(n, device=dev, dtype=torch.int64)[:, None, None] * (H * W)
+        w = torch.arange(W, device=dev, dtype=torch.int64)[None, :, None]
+        h = torch.arange(H, device=dev, dtype=torch.int64)[None, None, :] * W
+        _IDX_CACHE[key] = (t + w + h).to(torch.int32).reshape(n * W, H).contiguous()
+    return _IDX_CACHE[key]
+
+
+@torch.no_grad()
+def mag1c_tiles(cube, template, band_slice, num_iter=30, alpha=0.):
+    """cube: (n, H, W, C) BIP radiance on the GPU (process_aviris.py:183-184); the filter runs on the
+    contiguous window ``band_slice`` with one group per image column (identity GLT), straight from
+    the cube's memory (no band gather, no transpose).  -> (mf, albedo), each (n, H, W)."""
+    if not cube.is_cuda:
+        raise _lib.StarcopB200Error("starcop_b200 runs on CUDA tensors only (no CPU path)")
+    cube = cube.contiguous()
+    n, H, W, C = cube.shape
+    S = band_slice.stop - band_slice.start
+    idx = _column_groups(n, H, W, cube.device)
+    mf = torch.empty(n, H, W, dtype=cube.dtype, device=cube.device)
+    al = torch.empty_like(mf)
+    xw = cube.view(-1)[band_slice.start:]          # same storage, offset to the first window band
+    _filter(xw, C, idx, None, template, mf, al, S, num_iter, alpha)
+    return mf, al

@@ -168,6 +168,43 @@ class HyperStarcopUnet(UnetParameters):
                 out = self._forward_impl(x, _norm, self.training, record=False)
         return out[0] if squeeze else out
 
+    # ---- roofline probe: the dominant kernel timed alone, live, with CUDA events -----------------
+    def bench_dominant_kernel(self, batch, size, iters=20):
+        """decoder.blocks.0.conv1 (1376 -> 256 channels, 3x3, at 1/16 resolution): the largest single
+        kernel of the step (6.49 GFLOP/tile fprop).  Returns the roofline dict."""
+        self._materialize()
+        dev = self._flat[0].device
+        N, H, W, cin, cout, k = batch, size // 16, size // 16, 1376, 256, 3
+        w = dict(self.named_parameters())["decoder.blocks.0.conv1.0.weight"].data
+        lib = _lib.load()
+        if not lib.sc_tc_supported() or W % 16 or H % 8:
+            return None
+        cpad = lib.sc_tc_cin_pad(cin)
+        wb = torch.empty(cout * k * k * cpad, dtype=torch.bfloat16, device=dev)
+        st = _stream(dev)
+        _lib.call("sc_tc_pack_weights", w.data_ptr(), wb.data_ptr(), cout, cin, k, k, 0, cpad, cout, st)
+        # rotate over several input/output buffers so successive launches do not hit a warm L2
+        nbuf = 8
+        xs = [torch.randn(N, H, W, cin, device=dev).to(torch.bfloat16) for _ in range(nbuf)]
+        ys = [torch.empty(N, H, W, cout, dtype=torch.bfloat16, device=dev) for _ in range(nbuf)]
+        def launch(i):
+            _lib.call("sc_tc_conv_fprop", xs[i % nbuf].data_ptr(), cin, wb.data_ptr(), ys[i % nbuf].data_ptr(), cout, 0, 0,
+                      N, H, W, cin, cout, k, k, 1, 0, st)
+        for i in range(3):
+            launch(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            launch(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        flops = 2.0 * N * H * W * k * k * cin * cout
+        return {"bound": "tensor", "kernel": "tc_conv_fprop_kernel<32> (decoder.blocks.0.conv1 fprop)",
+                "achieved": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "flop_per_launch": flops,
+                "us_per_launch": ms * 1e3, "traffic": None}
+
     # ---- fused optimiser (Adam on the flat arena) -----------------------------------------------
     def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
         self._materialize()

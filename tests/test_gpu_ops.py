@@ -7,7 +7,7 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 from starcop_b200 import _lib  # noqa: E402
-from starcop_b200._lib import ACT_NONE, ACT_RELU, ACT_RELU6, SC_BF16, SC_F32, call  # noqa: E402
+from starcop_b200._lib import ACT_NONE, ACT_RELU, ACT_RELU6, SC_BF16, SC_F32, call, load  # noqa: E402
 
 DEV = "cuda"
 TDT = {SC_F32: torch.float32, SC_BF16: torch.bfloat16}
@@ -98,7 +98,8 @@ def test_depthwise(dtype, c, stride, hw, fused):
     call("sc_dwconv_dgrad", dy.data_ptr(), c, w.data_ptr(), dx.data_ptr(), c, N, hw, hw, c, stride, dtype, st())
     assert torch.allclose(nchw(dx), gin[0], **tol(dtype))
     dw = torch.zeros_like(w)
-    call("sc_dwconv_wgrad", xh.data_ptr(), c, sp, hp, act, dy.data_ptr(), c, dw.data_ptr(), N, hw, hw, c, stride, dtype, st())
+    ws = torch.empty(load().sc_dwconv_wgrad_workspace_bytes(c) // 4, device=DEV)
+    call("sc_dwconv_wgrad", xh.data_ptr(), c, sp, hp, act, dy.data_ptr(), c, dw.data_ptr(), ws.data_ptr(), N, hw, hw, c, stride, dtype, st())
     assert (dw - gin[1]).abs().max().item() <= (1e-4 if dtype == SC_F32 else 2e-2) * gin[1].abs().max().item()
 
 
@@ -125,10 +126,13 @@ def test_batchnorm_train_forward_backward(dtype, c, hw, act, up2, res):
     if up2:
         zr = F.interpolate(zr, scale_factor=2, mode="nearest")
     P = N * hw * hw
-    sums = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
-    call("sc_bn_stats", yh.data_ptr(), c, sums.data_ptr(), P, c, dtype, st())
+    import ctypes
+    sums = torch.full((load().sc_bn_partials_bytes(c) // 8,), float("nan"), dtype=torch.float64, device=DEV)
+    nrows = ctypes.c_int(0)
+    call("sc_bn_stats", yh.data_ptr(), c, sums.data_ptr(), ctypes.byref(nrows), P, c, dtype, st())
+    assert 1 <= nrows.value <= 296
     scale, shift, mean, invstd = (torch.empty(c, device=DEV) for _ in range(4))
-    call("sc_bn_finalize", sums.data_ptr(), P, c, bn.weight.data_ptr(), bn.bias.data_ptr(), rm.data_ptr(), rv.data_ptr(),
+    call("sc_bn_finalize", sums.data_ptr(), nrows.value, P, c, bn.weight.data_ptr(), bn.bias.data_ptr(), rm.data_ptr(), rv.data_ptr(),
          0.1, 1e-5, 1, scale.data_ptr(), shift.data_ptr(), mean.data_ptr(), invstd.data_ptr(), st())
     assert torch.allclose(rm, bn.running_mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(rv, bn.running_var, rtol=1e-5, atol=1e-6)
@@ -140,13 +144,13 @@ def test_batchnorm_train_forward_backward(dtype, c, hw, act, up2, res):
     # backward
     dz = nhwc(torch.randn_like(zr), dtype)
     gy, gw, gb = torch.autograd.grad(zr, [yr, bn.weight, bn.bias], dz.float().permute(0, 3, 1, 2))
-    red = torch.zeros(2 * c, dtype=torch.float64, device=DEV)
+    red = torch.full((load().sc_bn_partials_bytes(c) // 8,), float("nan"), dtype=torch.float64, device=DEV)
     call("sc_bn_bwd_reduce", dz.data_ptr(), c, int(up2), yh.data_ptr(), c, scale.data_ptr(), shift.data_ptr(),
-         mean.data_ptr(), invstd.data_ptr(), act, red.data_ptr(), N, hw, hw, c, dtype, st())
+         mean.data_ptr(), invstd.data_ptr(), act, red.data_ptr(), ctypes.byref(nrows), N, hw, hw, c, dtype, st())
     dy = torch.empty(N, hw, hw, c, device=DEV, dtype=TDT[dtype])
     dg, db = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
     call("sc_bn_bwd_apply", dz.data_ptr(), c, int(up2), yh.data_ptr(), c, scale.data_ptr(), shift.data_ptr(),
-         mean.data_ptr(), invstd.data_ptr(), bn.weight.data_ptr(), act, red.data_ptr(), dy.data_ptr(), c,
+         mean.data_ptr(), invstd.data_ptr(), bn.weight.data_ptr(), act, red.data_ptr(), nrows.value, dy.data_ptr(), c,
          dg.data_ptr(), db.data_ptr(), N, hw, hw, c, dtype, st())
     t = dict(rtol=1e-4, atol=1e-4) if dtype == SC_F32 else dict(rtol=5e-2, atol=5e-2)
     assert torch.allclose(nchw(dy), gy, **t)
@@ -159,7 +163,7 @@ def test_bn_eval_uses_running_stats():
     rm, rv = torch.randn(c, device=DEV), torch.rand(c, device=DEV) + 0.5
     g, b = torch.rand(c, device=DEV) + 0.5, torch.randn(c, device=DEV)
     scale, shift = torch.empty(c, device=DEV), torch.empty(c, device=DEV)
-    call("sc_bn_finalize", 0, 100, c, g.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(), 0.1, 1e-5, 0,
+    call("sc_bn_finalize", 0, 0, 100, c, g.data_ptr(), b.data_ptr(), rm.data_ptr(), rv.data_ptr(), 0.1, 1e-5, 0,
          scale.data_ptr(), shift.data_ptr(), 0, 0, st())
     x = torch.randn(2, c, 4, 4, device=DEV)
     ref = F.batch_norm(x, rm, rv, g, b, False, 0.1, 1e-5)

@@ -26,6 +26,9 @@ CASES = [  # N, H, W, Cin, Cout, k
     (1, 8, 16, 256, 1376, 3),     # its dgrad: 6 N tiles, ragged last tile
     (3, 32, 32, 80, 32, 3),       # many tiles, 2 accumulator stages, persistent loop
     (2, 16, 16, 320, 1280, 1),    # features.18
+    (2, 16, 16, 152, 64, 3),      # decoder block 2 conv1: Cin % 16 != 0 (last chunk zero-filled by TMA)
+    (2, 16, 16, 96, 24, 1),       # Cout % 16 != 0 (masked half tile)
+    (2, 16, 16, 24, 144, 1),
 ]
 
 
@@ -41,14 +44,17 @@ def make(N, H, W, Cin, Cout, k, seed=0):
 def test_tc_fprop(N, H, W, Cin, Cout, k, with_stats):
     assert load().sc_tc_supported() == 1
     x, w = make(N, H, W, Cin, Cout, k)
-    wb = torch.empty(Cout * k * k * Cin, device=DEV, dtype=torch.bfloat16)
-    call("sc_tc_pack_weights", w.data_ptr(), wb.data_ptr(), Cout, Cin, k, k, 0, Cin, Cout, st())
-    wq = wb.view(Cout, k, k, Cin).permute(0, 3, 1, 2).float()
+    cpad = load().sc_tc_cin_pad(Cin)
+    wb = torch.empty(Cout * k * k * cpad, device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_pack_weights", w.data_ptr(), wb.data_ptr(), Cout, Cin, k, k, 0, cpad, Cout, st())
+    wq = wb.view(Cout, k, k, cpad).permute(0, 3, 1, 2).float()[:, :Cin].contiguous()
     assert torch.equal(wq, w.to(torch.bfloat16).float())
     y = torch.full((N, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
-    stats = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
-    call("sc_tc_conv_fprop", x.data_ptr(), Cin, wb.data_ptr(), y.data_ptr(), Cout, stats.data_ptr() if with_stats else 0,
-         N, H, W, Cin, Cout, k, k, st())
+    import ctypes
+    part = torch.full((load().sc_bn_partials_bytes(Cout) // 8,), float("nan"), dtype=torch.float64, device=DEV)
+    nrows = ctypes.c_int(0)
+    call("sc_tc_conv_fprop", x.data_ptr(), Cin, wb.data_ptr(), y.data_ptr(), Cout, part.data_ptr() if with_stats else 0,
+         ctypes.byref(nrows), N, H, W, Cin, Cout, k, k, 1, 0, st())
     torch.cuda.synchronize()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), wq, padding=k // 2).permute(0, 2, 3, 1)
     err = (y.float() - ref).abs().max().item()
@@ -57,22 +63,28 @@ def test_tc_fprop(N, H, W, Cin, Cout, k, with_stats):
     assert torch.allclose(y.float(), ref.to(torch.bfloat16).float(), rtol=1.6e-2, atol=1e-3)
     if with_stats:
         yf = y.double().reshape(-1, Cout)
+        stats = part[:nrows.value * 2 * Cout].view(nrows.value, 2 * Cout).sum(0)
         assert torch.allclose(stats[:Cout], yf.sum(0), rtol=1e-4, atol=1e-2)
         assert torch.allclose(stats[Cout:], (yf * yf).sum(0), rtol=1e-4, atol=1e-2)
 
 
-def test_tc_dgrad_via_flipped_weights():
-    N, H, W, Cin, Cout, k = 2, 16, 16, 64, 32, 3
+@pytest.mark.parametrize("Cin,Cout", [(64, 32), (152, 64), (24, 96)])
+def test_tc_dgrad_via_flipped_weights(Cin, Cout):
+    N, H, W, k = 2, 16, 16, 3
     x, w = make(N, H, W, Cin, Cout, k)
     dy = torch.randn(N, H, W, Cout, device=DEV).to(torch.bfloat16)
-    wt = torch.empty(Cin * k * k * Cout, device=DEV, dtype=torch.bfloat16)
-    call("sc_tc_pack_weights", w.data_ptr(), wt.data_ptr(), Cout, Cin, k, k, 1, Cin, Cout, st())
+    cpad = load().sc_tc_cin_pad(Cout)
+    wt = torch.empty(Cin * k * k * cpad, device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_pack_weights", w.data_ptr(), wt.data_ptr(), Cout, Cin, k, k, 1, Cin, cpad, st())
     dx = torch.empty(N, H, W, Cin, device=DEV, dtype=torch.bfloat16)
-    call("sc_tc_conv_fprop", dy.data_ptr(), Cout, wt.data_ptr(), dx.data_ptr(), Cin, 0, N, H, W, Cout, Cin, k, k, st())
+    call("sc_tc_conv_fprop", dy.data_ptr(), Cout, wt.data_ptr(), dx.data_ptr(), Cin, 0, 0, N, H, W, Cout, Cin, k, k, 1, 0, st())
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
     yr = F.conv2d(xr, w.to(torch.bfloat16).float(), padding=1)
     (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 3, 1, 2))
     assert torch.allclose(dx.float(), gx.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
+    # accumulate: dx += dgrad
+    call("sc_tc_conv_fprop", dy.data_ptr(), Cout, wt.data_ptr(), dx.data_ptr(), Cin, 0, 0, N, H, W, Cout, Cin, k, k, 1, 1, st())
+    assert torch.allclose(dx.float(), 2 * gx.permute(0, 2, 3, 1), rtol=3e-2, atol=4e-2)
 
 
 @pytest.mark.parametrize("N,H,W,Cin,Cout,k", CASES + [(16, 64, 64, 32, 16, 3), (4, 32, 32, 16, 16, 3)])
@@ -80,10 +92,33 @@ def test_tc_wgrad(N, H, W, Cin, Cout, k):
     x, w = make(N, H, W, Cin, Cout, k, seed=1)
     dy = torch.randn(N, H, W, Cout, device=DEV).to(torch.bfloat16)
     dw = torch.zeros(Cout, Cin, k, k, device=DEV)
-    call("sc_tc_conv_wgrad", x.data_ptr(), Cin, dy.data_ptr(), Cout, dw.data_ptr(), N, H, W, Cin, Cout, k, k, st())
+    call("sc_tc_conv_wgrad", x.data_ptr(), Cin, dy.data_ptr(), Cout, dw.data_ptr(), N, H, W, Cin, Cout, k, k, 1, st())
     torch.cuda.synchronize()
     wr = w.clone().requires_grad_(True)
     yr = F.conv2d(x.float().permute(0, 3, 1, 2), wr, padding=k // 2)
     (gw,) = torch.autograd.grad(yr, wr, dy.float().permute(0, 3, 1, 2))
     err = (dw - gw).abs().max().item()
     assert err <= 2e-3 * gw.abs().max().item(), (err, gw.abs().max().item())
+
+
+def test_tc_stem_stride2_fprop_and_wgrad():
+    """encoder stem: Conv2d(4, 32, 3, stride 2, pad 1) on an input stored with 8-channel stride."""
+    N, H, W, Cin, Cout, k = 2, 32, 64, 4, 32, 3
+    torch.manual_seed(3)
+    x8 = torch.zeros(N, H, W, 8, device=DEV, dtype=torch.bfloat16)
+    x8[..., :Cin] = torch.randn(N, H, W, Cin, device=DEV).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, k, k, device=DEV) / 6
+    cpad = load().sc_tc_cin_pad(Cin)
+    wb = torch.empty(Cout * k * k * cpad, device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_pack_weights", w.data_ptr(), wb.data_ptr(), Cout, Cin, k, k, 0, cpad, Cout, st())
+    y = torch.full((N, H // 2, W // 2, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_conv_fprop", x8.data_ptr(), 8, wb.data_ptr(), y.data_ptr(), Cout, 0, 0, N, H, W, Cin, Cout, k, k, 2, 0, st())
+    xr = x8[..., :Cin].float().permute(0, 3, 1, 2)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, stride=2, padding=1)
+    assert torch.allclose(y.float(), ref.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
+    dy = torch.randn(N, H // 2, W // 2, Cout, device=DEV).to(torch.bfloat16)
+    dw = torch.zeros(Cout, Cin, k, k, device=DEV)
+    call("sc_tc_conv_wgrad", x8.data_ptr(), 8, dy.data_ptr(), Cout, dw.data_ptr(), N, H, W, Cin, Cout, k, k, 2, st())
+    (gw,) = torch.autograd.grad(ref, wr, dy.float().permute(0, 3, 1, 2))
+    assert (dw - gw).abs().max().item() <= 2e-3 * gw.abs().max().item()
