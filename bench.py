@@ -62,7 +62,7 @@ class ClockSampler(threading.Thread):
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=20).stdout
                 f = [s.strip() for s in out.strip().split(",")]
                 if len(f) >= 6:
                     self.samples.append(f)
@@ -135,11 +135,10 @@ def main():
     from starcop_b200.model_setup import get_model
     from starcop_b200.settings import default_settings
 
+    from starcop_b200 import parallel
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    parallel.init_distributed("nccl")
     _lib.load()
 
     torch.manual_seed(0)                       # same initial weights on every rank (DDP broadcast equivalent)
@@ -150,11 +149,8 @@ def main():
     pinned = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in host.items()}
     resident = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in host.items()}
 
-    def grad_sync(flat):
-        if world > 1:
-            dist.all_reduce(flat)              # NCCL sum over NVLink; the mean is folded into Adam's grad_scale
-            return 1.0 / world
-        return 1.0
+    parallel.broadcast_parameters(model.network.flat_params, [b for _, b in model.network.named_buffers()])
+    grad_sync = parallel.GradSync(world)       # NCCL sum over NVLink; the mean is folded into Adam's grad_scale
 
     def step_resident():
         return model.train_step_fused(resident, grad_sync=grad_sync)

@@ -187,19 +187,25 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int th = t2 % p.tiles_h;
         int img = t2 / p.tiles_h;
         int n0 = nt * p.block_n;
+        const int w0 = (tw * 16) * p.stride - pad, h0 = (th * 8) * p.stride - pad;
+        const int group_tx = A_BYTES + p.block_n * ROW_BYTES;
+        int cc = 0, kw = 0, kh = 0;             // running (channel chunk, tap) of the next K group: no divisions
         for (int s0 = 0; s0 < ksteps; s0 += G) {
           const int g_here = min(G, ksteps - s0);
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
           uint8_t* sB = sA + G * A_BYTES;
-          mbar_arrive_expect_tx(&full[stage], g_here * (A_BYTES + p.block_n * ROW_BYTES));
+          mbar_arrive_expect_tx(&full[stage], g_here * group_tx);
           for (int g = 0; g < g_here; ++g) {
-            int ks = s0 + g;
-            int tap = ks / p.cchunks, cc = ks - tap * p.cchunks;
-            int dy = tap / p.KW - pad, dx = tap % p.KW - pad;
-            tma_load_4d(sA + g * A_BYTES, &tmA, cc * KC, (tw * 16) * p.stride + dx, (th * 8) * p.stride + dy, img,
-                        &full[stage]);
-            tma_load_2d(sB + g * B_BYTES, &tmB, ks * KC, n0, &full[stage]);
+            tma_load_4d(sA + g * A_BYTES, &tmA, cc * KC, w0 + kw, h0 + kh, img, &full[stage]);
+            tma_load_2d(sB + g * B_BYTES, &tmB, (s0 + g) * KC, n0, &full[stage]);
+            if (++cc == p.cchunks) {
+              cc = 0;
+              if (++kw == p.KW) {
+                kw = 0;
+                ++kh;
+              }
+            }
           }
           if (++stage == p.stages) {
             stage = 0;
@@ -351,7 +357,14 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
-static int pick_kc(int C) { return C % 64 == 0 ? 64 : (C % 32 == 0 ? 32 : 16); }
+// channel chunk = swizzle span of one TMA box: the widest of 64 / 32 / 16 whose zero padding of the
+// ragged last chunk stays small (padding costs MMA cycles only: TMA zero-fills out-of-range channels)
+static int pick_kc(int C) {
+  if (C <= 16) return 16;
+  int p64 = (C + 63) / 64 * 64;
+  if ((p64 - C) * 8 <= C) return 64;      // <= 12.5 % padding
+  return 32;
+}
 extern "C" int sc_tc_cin_pad(int Cin) {
   int kc = pick_kc(Cin);
   return (Cin + kc - 1) / kc * kc;
@@ -486,27 +499,42 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // this CTA's sub-blocks (channel offset, tap shift) are fixed: decode them once
+      int sc0[SUBS], sdx[SUBS], sdy[SUBS];
+#pragma unroll
+      for (int s = 0; s < SUBS; ++s) {
+        int j = mb * SUBS + s;
+        int tap = j / p.cchunks, cc = j - tap * p.cchunks;
+        sc0[s] = cc * KC;
+        sdy[s] = tap / p.KW - pad;
+        sdx[s] = tap % p.KW - pad;
+      }
+      const uint32_t tx = valid_subs * A_SUB_BYTES + B_BYTES;
+      int tw = t_begin % p.tiles_w;
+      int t2 = t_begin / p.tiles_w;
+      int th = t2 % p.tiles_h;
+      int img = t2 / p.tiles_h;
       for (int t = t_begin; t < t_end; ++t) {
-        int tw = t % p.tiles_w;
-        int t2 = t / p.tiles_w;
-        int th = t2 % p.tiles_h;
-        int img = t2 / p.tiles_h;
         mbar_wait(&empty[stage], phase ^ 1);
         uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
         uint8_t* sB = sA + A_BYTES;
-        mbar_arrive_expect_tx(&full[stage], valid_subs * A_SUB_BYTES + B_BYTES);
-        for (int s = 0; s < valid_subs; ++s) {
-          int j = mb * SUBS + s;
-          int tap = j / p.cchunks, cc = j - tap * p.cchunks;
-          int dy = tap / p.KW - pad, dx = tap % p.KW - pad;
-          tma_load_4d(sA + s * A_SUB_BYTES, &tmX, cc * KC, (tw * 16) * p.stride + dx, (th * 4) * p.stride + dy, img,
-                      &full[stage]);
-        }
+        mbar_arrive_expect_tx(&full[stage], tx);
+        const int wq = (tw * 16) * p.stride, hq = (th * 4) * p.stride;
+#pragma unroll
+        for (int s = 0; s < SUBS; ++s)
+          if (s < valid_subs) tma_load_4d(sA + s * A_SUB_BYTES, &tmX, sc0[s], wq + sdx[s], hq + sdy[s], img, &full[stage]);
         for (int b = 0; b < p.nb_boxes; ++b)
           tma_load_4d(sB + b * B_BOX_BYTES, &tmDY, n0 + b * p.kcb, tw * 16, th * 4, img, &full[stage]);
         if (++stage == p.stages) {
           stage = 0;
           phase ^= 1;
+        }
+        if (++tw == p.tiles_w) {
+          tw = 0;
+          if (++th == p.tiles_h) {
+            th = 0;
+            ++img;
+          }
         }
       }
     }

@@ -208,6 +208,9 @@ class UNetEngine:
             cpad = _lib.load().sc_tc_cin_pad(cin)
             wb = self.arena.alloc(cout * k * k * cpad * 2)
             call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, k, k, 0, cpad, cout, self.stream)
+            # the statistics epilogue costs ~(Cout/16) x 300 cycles per 128-pixel tile: worth fusing only
+            # when the tile's K loop is long enough to hide it, else the separate pass over y is cheaper
+            want_stats = want_stats and cin * k * k >= 256
             part, n = (self._partials(cout), ctypes.c_int(0)) if want_stats else (0, ctypes.c_int(0))
             call("sc_tc_conv_fprop", x.ptr, x.ld, wb, y.ptr, y.ld, part, ctypes.byref(n), x.N, x.H, x.W, cin, cout,
                  k, k, stride, 0, self.stream)
