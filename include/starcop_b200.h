@@ -152,7 +152,7 @@ int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float 
  * (-9999).  tmpl: S doubles.  mf_out / albedo_out: per-pixel outputs indexed by `pix` (scatter).
  * num_iter = 0 is the plain matched filter `rmf`; alpha = diagonal loading (mag1c.py:246).
  * status: optional device int, incremented per group whose covariance was not positive definite. */
-int64_t sc_mag1c_smem_bytes(int S);
+int64_t sc_mag1c_smem_bytes(int S, int pmax, int elem_bytes);   /* must be <= 220 KB */
 int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_t* pix_idx, const int32_t* counts,
                     int pmax, const double* tmpl, void* mf_out, void* albedo_out, int G, int S,
                     int num_iter, double alpha, int fp64, int* status, void* stream);

@@ -19,11 +19,21 @@ using namespace sc;
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kChunk = 32;          // pixels staged per shared-memory tile when accumulating X^T X
+constexpr int kTile = 32;           // pixels staged per shared-memory tile (double buffered)
 constexpr double kScaling = 1e5;    // mag1c.py:56
 constexpr double kEpsilon = 1e-9;   // mag1c.py:57
 
 __device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // j <= i
+
+// asynchronous global -> shared copies (LDGSTS): the whole tile is in flight at once, no registers
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "n"(BYTES)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ double block_sum(double v, double* red) {
   v = warp_sum(v);
@@ -35,52 +45,59 @@ __device__ double block_sum(double v, double* red) {
   return s;
 }
 
-// in-place packed Cholesky (lower), returns false through *ok when a pivot is not positive
-__device__ void cholesky_packed(double* A, int S, int* ok, const uchar2* __restrict__ rc) {
+// Left-looking Cholesky of the (S+1) x (S+1) matrix [[C, b], [b^T, .]] stored row-major with leading
+// dimension LD (LD = 1 mod 16: column accesses by consecutive threads are bank-conflict free for
+// doubles).  Thread i owns row i; row S holds b, so on exit it holds z = L^-1 b (the forward
+// substitution comes for free).  Only the lower triangle is referenced.
+__device__ void cholesky_aug(double* A, int S, int LD, int* ok, double* diag) {
+  const int i = threadIdx.x;
   for (int j = 0; j < S; ++j) {
+    double sdot = 0.0;
+    if (i >= j && i <= S) {
+      const double* ri = A + i * LD;
+      const double* rj = A + j * LD;
+      // four independent partial sums: the fp64 FMA chain is latency-, not throughput-bound
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      int k = 0;
+      for (; k + 4 <= j; k += 4) {
+        s0 += ri[k] * rj[k];
+        s1 += ri[k + 1] * rj[k + 1];
+        s2 += ri[k + 2] * rj[k + 2];
+        s3 += ri[k + 3] * rj[k + 3];
+      }
+      for (; k < j; ++k) s0 += ri[k] * rj[k];
+      sdot = ri[j] - ((s0 + s1) + (s2 + s3));
+      if (i == j) {
+        if (!(sdot > 0.0)) {
+          *ok = 0;
+          sdot = 1.0;
+        }
+        *diag = sqrt(sdot);
+      }
+    }
     __syncthreads();
-    double d = A[tri(j, j)];
-    if (threadIdx.x == 0 && !(d > 0.0)) *ok = 0;
-    double ljj = sqrt(d > 0.0 ? d : 1.0);
+    if (i >= j && i <= S) A[i * LD + j] = (i == j) ? *diag : sdot / *diag;
     __syncthreads();
-    // scale column j
-    for (int i = j + threadIdx.x; i < S; i += kThreads) A[tri(i, j)] = (i == j) ? ljj : A[tri(i, j)] / ljj;
-    __syncthreads();
-    // rank-1 update of the trailing lower triangle: A[i][k] -= L[i][j] * L[k][j], j < k <= i
-    const int n = S - j - 1;
-    const int cnt = n * (n + 1) / 2;
-    for (int e = threadIdx.x; e < cnt; e += kThreads) {
-      // e -> (r, c) with c <= r in the n x n trailing triangle (a prefix of the packed enumeration)
-      const uchar2 q = rc[e];
-      int i = j + 1 + q.x, k = j + 1 + q.y;
-      A[tri(i, k)] -= A[tri(i, j)] * A[tri(k, j)];
+  }
+}
+
+// backward substitution L^T c = z (z = row S of A), one warp; c_i = (z_i - sum_{k>i} L_ki c_k) / L_ii
+__device__ void chol_backsolve(const double* A, int S, int LD, double* c) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    const double* z = A + S * LD;
+    for (int i = S - 1; i >= 0; --i) {
+      double s = 0.0;
+      for (int k = i + 1 + lane; k < S; k += 32) s += A[k * LD + i] * c[k];
+      s = warp_sum(s);
+      if (lane == 0) c[i] = (z[i] - s) / A[i * LD + i];
+      __syncwarp();
     }
   }
   __syncthreads();
 }
 
-// solve L L^T c = b (packed L), result in c; z is scratch.  One warp does the substitutions.
-__device__ void chol_solve(const double* L, const double* b, double* z, double* c, int S) {
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int lane = threadIdx.x;
-    for (int i = 0; i < S; ++i) {           // forward: z_i = (b_i - sum_{k<i} L_ik z_k) / L_ii
-      double s = 0.0;
-      for (int k = lane; k < i; k += 32) s += L[tri(i, k)] * z[k];
-      s = warp_sum(s);
-      if (lane == 0) z[i] = (b[i] - s) / L[tri(i, i)];
-      __syncwarp();
-    }
-    for (int i = S - 1; i >= 0; --i) {      // backward: c_i = (z_i - sum_{k>i} L_ki c_k) / L_ii
-      double s = 0.0;
-      for (int k = i + 1 + lane; k < S; k += 32) s += L[tri(k, i)] * c[k];
-      s = warp_sum(s);
-      if (lane == 0) c[i] = (z[i] - s) / L[tri(i, i)];
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-}
+__host__ __device__ inline int mag1c_ld(int S) { return ((S + 1) + 14) / 16 * 16 + 1; }   // >= S+1, = 1 mod 16
 
 template <typename TS>
 __global__ void __launch_bounds__(kThreads)
@@ -93,9 +110,10 @@ mag1c_kernel(const TS* __restrict__ x, int64_t pixel_stride, const int32_t* __re
   if (P <= 10) return;                                 // mag1c.py:166-168: too few pixels, outputs stay NODATA
   const int32_t* idx = pix_idx + (int64_t)g * pmax;
   const int NT = S * (S + 1) / 2;
+  const int LD = mag1c_ld(S);
   double* XtX = smd;                 // packed lower triangle of sum x x^T
-  double* A = XtX + NT;              // working covariance / Cholesky factor
-  double* xbar = A + NT;
+  double* A = XtX + NT;              // (S+1) x LD working covariance / Cholesky factor, row S = rhs
+  double* xbar = A + (S + 1) * LD;
   double* mu = xbar + S;
   double* tprev = mu + S;            // target used inside modx
   double* tcur = tprev + S;          // target = template * mu
@@ -104,12 +122,14 @@ mag1c_kernel(const TS* __restrict__ x, int64_t pixel_stride, const int32_t* __re
   double* z = cit + S;
   double* tp = z + S;                // template
   double* red = tp + S;              // [8] block-reduction scratch
-  double* tiled = red + 8;                             // [kChunk][S] staging tile (fp64 view)
-  float* tile = reinterpret_cast<float*>(tiled);       // same storage, fp32 view
-  uchar2* rc = reinterpret_cast<uchar2*>(tiled + kChunk * S);   // packed index -> (row, col)
+  double* a_s = red + 8;             // [kTile] a = R*mf of the staged pixels
+  TS* tile0 = reinterpret_cast<TS*>(a_s + kTile);                 // 2 x [kTile][S] staged spectra (double buffer)
+  uchar2* rc = reinterpret_cast<uchar2*>(tile0 + 2 * kTile * S);  // packed index -> (row, col)
+  int32_t* pidx = reinterpret_cast<int32_t*>(rc + ((NT + 3) & ~3)); // [P] this group's pixel indices (8 B aligned)
+  TS* R_s = reinterpret_cast<TS*>(pidx + ((P + 1) & ~1));           // [P] albedo factor, storage precision
+  TS* mf_s = R_s + P;                                               // [P] current matched-filter value
   __shared__ int ok;
   const int tid = threadIdx.x;
-  constexpr bool kF64 = sizeof(TS) == 8;
 
   if (tid == 0) ok = 1;
   for (int i = tid; i < S; i += kThreads)
@@ -119,63 +139,78 @@ mag1c_kernel(const TS* __restrict__ x, int64_t pixel_stride, const int32_t* __re
     tp[i] = tmpl[i];
     xbar[i] = 0.0;
   }
+  for (int i = tid; i < P; i += kThreads) pidx[i] = idx[i];
   __syncthreads();
 
-  // ---- pass 0: xbar and X^T X, pixels staged kChunk at a time -------------------------------------
-  for (int p0 = 0; p0 < P; p0 += kChunk) {
-    const int np = min(kChunk, P - p0);
-    __syncthreads();
+  // stage pixels [p0, p0+np) of the group into buffer b with cp.async: consecutive threads copy
+  // consecutive bands of a pixel row; one commit group per tile
+  auto stage = [&](int b, int p0) {
+    const int np = min(kTile, P - p0);
+    TS* t = tile0 + b * kTile * S;
     for (int e = tid; e < np * S; e += kThreads) {
-      int pp = e / S, s = e - pp * S;
-      TS val = x[(int64_t)idx[p0 + pp] * pixel_stride + s];
-      if (kF64) tiled[pp * S + s] = (double)val;
-      else tile[pp * S + s] = (float)val;
+      int pp = e / S, s2 = e - pp * S;
+      cp_async<sizeof(TS)>(t + pp * S + s2, x + (int64_t)pidx[p0 + pp] * pixel_stride + s2);
+    }
+    cp_async_commit();
+  };
+  const int nchunks = (P + kTile - 1) / kTile;
+
+  // ---- pass 0: xbar and X^T X -----------------------------------------------------------------------
+  stage(0, 0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int p0 = c * kTile;
+    const int np = min(kTile, P - p0);
+    const TS* tile = tile0 + (c & 1) * kTile * S;
+    if (c + 1 < nchunks) {
+      stage((c + 1) & 1, p0 + kTile);     // prefetch the next tile while this one is consumed
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
     for (int e = tid; e < NT; e += kThreads) {
       const int i = rc[e].x, j = rc[e].y;
-      double acc = 0.0;
-      if (kF64) {
-        for (int pp = 0; pp < np; ++pp) acc += tiled[pp * S + i] * tiled[pp * S + j];
-      } else {
-        for (int pp = 0; pp < np; ++pp) acc += (double)tile[pp * S + i] * (double)tile[pp * S + j];
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int pp = 0;
+      for (; pp + 4 <= np; pp += 4) {
+        a0 += (double)tile[pp * S + i] * (double)tile[pp * S + j];
+        a1 += (double)tile[(pp + 1) * S + i] * (double)tile[(pp + 1) * S + j];
+        a2 += (double)tile[(pp + 2) * S + i] * (double)tile[(pp + 2) * S + j];
+        a3 += (double)tile[(pp + 3) * S + i] * (double)tile[(pp + 3) * S + j];
       }
-      XtX[e] += acc;
+      for (; pp < np; ++pp) a0 += (double)tile[pp * S + i] * (double)tile[pp * S + j];
+      XtX[e] += (a0 + a1) + (a2 + a3);
     }
-    for (int s = tid; s < S; s += kThreads) {
+    for (int s2 = tid; s2 < S; s2 += kThreads) {
       double acc = 0.0;
-      if (kF64) {
-        for (int pp = 0; pp < np; ++pp) acc += tiled[pp * S + s];
-      } else {
-        for (int pp = 0; pp < np; ++pp) acc += (double)tile[pp * S + s];
-      }
-      xbar[s] += acc;
+      for (int pp = 0; pp < np; ++pp) acc += (double)tile[pp * S + s2];
+      xbar[s2] += acc;
     }
+    __syncthreads();                        // everyone done with this buffer before it is refilled
   }
-  __syncthreads();
   const double N = (double)P;
-  for (int s = tid; s < S; s += kThreads) {
-    xbar[s] /= N;
-    mu[s] = xbar[s];
-    tcur[s] = tp[s] * xbar[s];      // target0 = template * mean(x)   (mag1c.py:312, :233)
-    tprev[s] = 0.0;
-    v[s] = 0.0;
+  for (int s2 = tid; s2 < S; s2 += kThreads) {
+    xbar[s2] /= N;
+    mu[s2] = xbar[s2];
+    tcur[s2] = tp[s2] * xbar[s2];      // target0 = template * mean(x)   (mag1c.py:312, :233)
+    tprev[s2] = 0.0;
+    v[s2] = 0.0;
   }
   __syncthreads();
   double mumu = 0.0;
-  for (int s = 0; s < S; ++s) mumu += xbar[s] * xbar[s];   // every thread: mu.mu for the albedo factor
+  for (int s2 = 0; s2 < S; ++s2) mumu += xbar[s2] * xbar[s2];   // every thread: mu.mu for the albedo factor
 
   double sum_a = 0.0, sum_a2 = 0.0;       // block-uniform after block_sum
   for (int it = 0; it <= num_iter; ++it) {
     // ---- covariance of modx, C = (1-alpha) S + alpha diag(S) ------------------------------------
     if (it > 0) {
       const double ma = sum_a / N;
-      for (int s = tid; s < S; s += kThreads) {
-        tprev[s] = tcur[s];
-        mu[s] = xbar[s] - ma * tcur[s];
+      for (int s2 = tid; s2 < S; s2 += kThreads) {
+        tprev[s2] = tcur[s2];
+        mu[s2] = xbar[s2] - ma * tcur[s2];
       }
       __syncthreads();
-      for (int s = tid; s < S; s += kThreads) tcur[s] = tp[s] * mu[s];
+      for (int s2 = tid; s2 < S; s2 += kThreads) tcur[s2] = tp[s2] * mu[s2];
       __syncthreads();
     }
     for (int e = tid; e < NT; e += kThreads) {
@@ -184,60 +219,101 @@ mag1c_kernel(const TS* __restrict__ x, int64_t pixel_stride, const int32_t* __re
       if (it > 0) sxx += -v[i] * tprev[j] - tprev[i] * v[j] + sum_a2 * tprev[i] * tprev[j];
       double c = sxx / N - mu[i] * mu[j];
       if (i != j) c *= (1.0 - alpha);
-      A[e] = c;
+      A[i * LD + j] = c;
     }
-    cholesky_packed(A, S, &ok, rc);
-    chol_solve(A, tcur, z, cit, S);
+    for (int s2 = tid; s2 < S; s2 += kThreads) A[S * LD + s2] = tcur[s2];
+    __syncthreads();
+    cholesky_aug(A, S, LD, &ok, z);
+    chol_backsolve(A, S, LD, cit);
     double nrm = 0.0, mucit = 0.0;
-    for (int s = 0; s < S; ++s) {
-      nrm += tcur[s] * cit[s];
-      mucit += mu[s] * cit[s];
+    for (int s2 = 0; s2 < S; ++s2) {
+      nrm += tcur[s2] * cit[s2];
+      mucit += mu[s2] * cit[s2];
     }
     if (it > 0 && nrm < 1.0) nrm = 1.0;               // mag1c.py:264-266 (not applied inside rmf)
-    // ---- apply: one thread per pixel -------------------------------------------------------------
+    // ---- apply + next iteration's statistics, kTile staged pixels at a time ------------------------
+    const bool last = it == num_iter;
     double la = 0.0, la2 = 0.0;
-    for (int p = tid; p < P; p += kThreads) {
-      const int64_t pix = idx[p];
-      const TS* xp = x + pix * pixel_stride;
-      double dot = 0.0, xmu = 0.0;
-      for (int s = 0; s < S; ++s) {
-        double xv = (double)xp[s];
-        dot += xv * cit[s];
-        if (it == 0) xmu += xv * xbar[s];
-      }
-      double R, mf;
-      if (it == 0) {
-        R = xmu / mumu;                                // mag1c.py:330
-        mf = (dot - mucit) / (R * nrm);                // mag1c.py:332
+    double vacc = 0.0;                                // thread s2 = tid < S owns v[s2]
+    stage(0, 0);
+    for (int c = 0; c < nchunks; ++c) {
+      const int p0 = c * kTile;
+      const int np = min(kTile, P - p0);
+      const TS* tile = tile0 + (c & 1) * kTile * S;
+      if (c + 1 < nchunks) {
+        stage((c + 1) & 1, p0 + kTile);
+        cp_async_wait<1>();
       } else {
-        R = (double)al_out[pix];
-        double mf_old = (double)mf_out[pix];
-        double reg = 1.0 / (R * (mf_old + kEpsilon));  // mag1c.py:255
-        mf = ((dot - mucit) - reg) / (R * nrm);        // mag1c.py:267
+        cp_async_wait<0>();
       }
-      mf = mf > 0.0 ? mf : 0.0;                        // relu
-      if (it == 0) al_out[pix] = (TS)R;
-      // keep the working value in the storage precision, like the reference's tensors
-      TS mfs = (TS)mf;
-      mf_out[pix] = it == num_iter ? (TS)((double)mfs * kScaling) : mfs;
-      double a = (double)(TS)R * (double)mfs;
-      la += a;
-      la2 += a * a;
+      __syncthreads();
+      for (int pp = tid; pp < np; pp += kThreads) {   // one thread per staged pixel (row stride S is odd: no conflicts)
+        const int64_t pix = pidx[p0 + pp];
+        const TS* xp = tile + pp * S;
+        double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0, xmu = 0.0;
+        int s2 = 0;
+        for (; s2 + 4 <= S; s2 += 4) {
+          d0 += (double)xp[s2] * cit[s2];
+          d1 += (double)xp[s2 + 1] * cit[s2 + 1];
+          d2 += (double)xp[s2 + 2] * cit[s2 + 2];
+          d3 += (double)xp[s2 + 3] * cit[s2 + 3];
+        }
+        for (; s2 < S; ++s2) d0 += (double)xp[s2] * cit[s2];
+        const double dot = (d0 + d1) + (d2 + d3);
+        if (it == 0) {
+          double x0 = 0.0, x1 = 0.0;
+          for (s2 = 0; s2 + 2 <= S; s2 += 2) {
+            x0 += (double)xp[s2] * xbar[s2];
+            x1 += (double)xp[s2 + 1] * xbar[s2 + 1];
+          }
+          for (; s2 < S; ++s2) x0 += (double)xp[s2] * xbar[s2];
+          xmu = x0 + x1;
+        }
+        double R, mf;
+        if (it == 0) {
+          R = xmu / mumu;                                // mag1c.py:330
+          mf = (dot - mucit) / (R * nrm);                // mag1c.py:332
+        } else {
+          R = (double)R_s[p0 + pp];
+          double mf_old = (double)mf_s[p0 + pp];
+          double reg = 1.0 / (R * (mf_old + kEpsilon));  // mag1c.py:255
+          mf = ((dot - mucit) - reg) / (R * nrm);        // mag1c.py:267
+        }
+        mf = mf > 0.0 ? mf : 0.0;                        // relu
+        TS mfs = (TS)mf;                                 // working values kept in the storage precision
+        if (it == 0) {
+          R_s[p0 + pp] = (TS)R;
+          al_out[pix] = (TS)R;
+        }
+        mf_s[p0 + pp] = mfs;
+        if (last) mf_out[pix] = (TS)((double)mfs * kScaling);
+        double a = (double)(TS)R * (double)mfs;
+        a_s[pp] = a;
+        la += a;
+        la2 += a * a;
+      }
+      __syncthreads();
+      if (!last && tid < S) {
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+        int pp = 0;
+        for (; pp + 4 <= np; pp += 4) {
+          v0 += a_s[pp] * (double)tile[pp * S + tid];
+          v1 += a_s[pp + 1] * (double)tile[(pp + 1) * S + tid];
+          v2 += a_s[pp + 2] * (double)tile[(pp + 2) * S + tid];
+          v3 += a_s[pp + 3] * (double)tile[(pp + 3) * S + tid];
+        }
+        for (; pp < np; ++pp) v0 += a_s[pp] * (double)tile[pp * S + tid];
+        vacc += (v0 + v1) + (v2 + v3);
+      }
+      __syncthreads();                      // buffer and a_s free for the next tile
     }
-    if (it == num_iter) break;
+    if (last) break;
+    __syncthreads();
+    for (int s2 = tid; s2 < S; s2 += kThreads) {
+      if (s2 == tid) v[s2] = vacc;
+    }
     sum_a = block_sum(la, red);
     sum_a2 = block_sum(la2, red);
-    __syncthreads();                                   // mf_out / al_out of this block visible below
-    // ---- v = X^T a: one thread per band, pixels streamed (x rows are L1/L2 resident) ---------------
-    for (int s = tid; s < S; s += kThreads) {
-      double acc = 0.0;
-      for (int p = 0; p < P; ++p) {
-        const int64_t pix = idx[p];
-        double a = (double)al_out[pix] * (double)mf_out[pix];
-        acc += a * (double)x[pix * pixel_stride + s];
-      }
-      v[s] = acc;
-    }
     __syncthreads();
   }
   if (tid == 0 && !ok && status) atomicAdd(status, 1);
@@ -245,17 +321,17 @@ mag1c_kernel(const TS* __restrict__ x, int64_t pixel_stride, const int32_t* __re
 
 }  // namespace
 
-extern "C" int64_t sc_mag1c_smem_bytes(int S) {
+extern "C" int64_t sc_mag1c_smem_bytes(int S, int pmax, int elem_bytes) {
   int64_t NT = (int64_t)S * (S + 1) / 2;
-  return (2 * NT + 8 * S + 8) * 8 + (int64_t)kChunk * S * 8 + 2 * NT + 16;
+  return (NT + (int64_t)(S + 1) * mag1c_ld(S) + 8 * S + 8 + kTile) * 8 + 2 * (int64_t)kTile * S * elem_bytes + 2 * NT + 32 + (4 + 2 * (int64_t)elem_bytes) * (pmax + 2);
 }
 
 extern "C" int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_t* pix_idx, const int32_t* counts,
                                int pmax, const double* tmpl, void* mf_out, void* albedo_out, int G, int S,
                                int num_iter, double alpha, int fp64, int* status, void* stream) {
-  if (!x || !pix_idx || !tmpl || !mf_out || !albedo_out || G <= 0 || S < 2 || S > 160 || pmax < 1 || num_iter < 0)
+  if (!x || !pix_idx || !tmpl || !mf_out || !albedo_out || G <= 0 || S < 2 || S + 1 > kThreads || pmax < 1 || num_iter < 0)
     return SC_ERR_BAD_ARG;
-  size_t smem = (size_t)sc_mag1c_smem_bytes(S);
+  size_t smem = (size_t)sc_mag1c_smem_bytes(S, pmax, fp64 ? 8 : 4);
   if (smem > 220 * 1024) return SC_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
