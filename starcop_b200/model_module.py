@@ -201,9 +201,13 @@ class HyperStarcopUnet(UnetParameters):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         flops = 2.0 * N * H * W * k * k * cin * cout
-        return {"bound": "tensor", "kernel": "tc_conv_fprop_kernel<32> (decoder.blocks.0.conv1 fprop)",
+        # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed
+        # `ncu --set full` capture (profiles/r01_b0c1_fprop_ncu_full.json), valid for bs=16 / 512x512 only
+        traffic = 51.78e6 if (batch, size) == (16, 512) else None
+        return {"bound": "tensor", "kernel": "tc_conv_fprop_kernel<64> (decoder.blocks.0.conv1 fprop)",
                 "achieved": flops / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "flop_per_launch": flops,
-                "us_per_launch": ms * 1e3, "traffic": None}
+                "us_per_launch": ms * 1e3, "traffic": traffic, "traffic_unit": "bytes/launch",
+                "algorithmic_bytes": 2.0 * N * H * W * (cin + cout) + 2.0 * cout * k * k * cpad}
 
     # ---- fused optimiser (Adam on the flat arena) -----------------------------------------------
     def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
