@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     return ap.parse_args()
 
 
@@ -152,17 +153,25 @@ def main():
     parallel.broadcast_parameters(model.network.flat_params, [b for _, b in model.network.named_buffers()])
     grad_sync = parallel.GradSync(world)       # NCCL sum over NVLink; the mean is folded into Adam's grad_scale
 
+    # the whole step (forward, loss, backward, all-reduce, Adam) replayed as one CUDA graph
+    graphed = None if args.no_graph else model.make_graphed_train_step(resident, grad_sync=grad_sync)
+
     def step_resident():
+        if graphed is not None:
+            return graphed(resident)
         return model.train_step_fused(resident, grad_sync=grad_sync)
 
     staging = {k: torch.empty_like(v, device=dev) for k, v in host.items() if torch.is_tensor(v)}
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
 
     def step_e2e():
-        for k, v in pinned.items():
-            if torch.is_tensor(v):
-                staging[k].copy_(v, non_blocking=True)
-        loss = model.train_step_fused(staging, grad_sync=grad_sync)
+        if graphed is not None:
+            loss = graphed(pinned)                 # H2D copies from pinned memory into the graph's static inputs
+        else:
+            for k, v in pinned.items():
+                if torch.is_tensor(v):
+                    staging[k].copy_(v, non_blocking=True)
+            loss = model.train_step_fused(staging, grad_sync=grad_sync)
         loss_host.copy_(loss.reshape(1), non_blocking=True)
         return loss
 
@@ -191,7 +200,14 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    launches_per_step = None
+    if graphed is not None:                     # kernel launches inside the graph = C-ABI calls of one eager step
+        c0 = _lib.launch_count()
+        model.train_step_fused(resident, grad_sync=grad_sync)
+        launches_per_step = _lib.launch_count() - c0
     ms, launches = timed(step_resident, args.steps, max(args.warmup, 3))
+    if launches_per_step is not None:
+        launches = launches_per_step * args.steps
     ms_e2e, _ = timed(step_e2e, args.steps, 1)
     sampler.stop_flag = True
 

@@ -141,6 +141,10 @@ int sc_bce_fused(const float* logits, const float* y, const float* w, float pos_
  * step_host is the 1-based step count; grad_scale multiplies g first (DDP mean). */
 int sc_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
                  float beta2, float eps, int step_host, float grad_scale, void* stream);
+/* same update with the step counter (incremented here) and the learning rate in device memory, so a
+ * captured CUDA graph of the train step stays valid across steps and lr-scheduler changes */
+int sc_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev,
+                     float beta1, float beta2, float eps, int* step_dev, float grad_scale, void* stream);
 
 /* ---- A8/A10: mag1c matched filter (starcop/models/mag1c.py:176-348) -------------------------
  * One pixel group per CTA (a detector column of a tile, process_aviris.py:211-212, or any pixel set

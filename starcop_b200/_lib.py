@@ -37,6 +37,7 @@ SIGNATURES = {
     "sc_head_bwd": [P, I, P, P, P, I, P, P, I, I, I, I, I, P],
     "sc_bce_fused": [P, P, P, F, I, L, F, P, P, P, P, P, P, P, P, P, P, P, P],
     "sc_adam_step": [P, P, P, P, L, F, F, F, F, I, F, P],
+    "sc_adam_step_dev": [P, P, P, P, L, P, F, F, F, P, F, P],
     "sc_mag1c_smem_bytes": [I, I, I],
     "sc_mag1c_filter": [P, L, P, P, I, P, P, P, I, I, I, D, I, P, P],
     "sc_ratio_workspace_bytes": [I, L],

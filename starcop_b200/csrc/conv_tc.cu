@@ -133,6 +133,7 @@ struct FpropParams {
 };
 
 constexpr int kTcThreads = 192;
+constexpr int kMaxDynSmem = 227 * 1024;
 
 template <int KC>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -420,9 +421,13 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FPROP(KC)                                                                                     \
   do {                                                                                                       \
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_fprop_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem);                                                         \
-    if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                          \
+    static bool attr_set = false; /* opt in once to the full dynamic shared memory (not a stream op) */      \
+    if (!attr_set) {                                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(tc_conv_fprop_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           kMaxDynSmem);                                                     \
+      if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                        \
+      attr_set = true;                                                                                       \
+    }                                                                                                        \
     tc_conv_fprop_kernel<KC><<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);                                   \
   } while (0)
   if (kc == 64) LAUNCH_FPROP(64);
@@ -649,9 +654,13 @@ extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_WGRAD(KC)                                                                                     \
   do {                                                                                                       \
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem);                                                         \
-    if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                          \
+    static bool attr_set = false;                                                                            \
+    if (!attr_set) {                                                                                         \
+      cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           kMaxDynSmem);                                                     \
+      if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                        \
+      attr_set = true;                                                                                       \
+    }                                                                                                        \
     tc_conv_wgrad_kernel<KC><<<grid, kTcThreads, smem, st>>>(tmX, tmDY, p);                                  \
   } while (0)
   if (kc == 64) LAUNCH_WGRAD(64);

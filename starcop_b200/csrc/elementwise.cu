@@ -92,22 +92,36 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __rest
   for (int i = threadIdx.x; i < 2 * CVB * 8; i += blockDim.x) sm[i] = 0.0;
   __syncthreads();
   if (pl < PL && cv * 8 < C) {
+    // fp32 partial sums over runs of 16 pixels, flushed into fp64 accumulators (keeps the fp64 pipe idle)
     double s[8], q[8];
+    float fs[8], fq[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      s[i] = q[i] = 0.0;
+      fs[i] = fq[i] = 0.f;
+    }
+    int run = 0;
     for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
       f8 v = load8<T>(y + p * ldy + cv * 8);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        double d = (double)v.v[i];
-        s[i] += d;
-        q[i] += d * d;
+        fs[i] += v.v[i];
+        fq[i] = fmaf(v.v[i], v.v[i], fq[i]);
+      }
+      if (++run == 16) {
+        run = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += (double)fs[i];
+          q[i] += (double)fq[i];
+          fs[i] = fq[i] = 0.f;
+        }
       }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sm[cvl * 8 + i], s[i]);
-      atomicAdd(&sm[CVB * 8 + cvl * 8 + i], q[i]);
+      atomicAdd(&sm[cvl * 8 + i], s[i] + (double)fs[i]);
+      atomicAdd(&sm[CVB * 8 + cvl * 8 + i], q[i] + (double)fq[i]);
     }
   }
   __syncthreads();
@@ -121,7 +135,7 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __rest
   }
 }
 
-extern "C" int64_t sc_bn_partials_bytes(int C) { return (int64_t)(SC_BN_MAX_PARTIALS + 1) * 2 * C * sizeof(double); }
+extern "C" int64_t sc_bn_partials_bytes(int C) { return (int64_t)(SC_BN_MAX_PARTIALS + 2) * 2 * C * sizeof(double); }
 
 extern "C" int sc_bn_stats(const void* y, int ldy, double* partials, int* nrows_host, int64_t P, int C, int dtype,
                            void* stream) {
@@ -197,16 +211,22 @@ extern "C" int sc_bn_finalize(const double* sums, int nrows, int64_t P, int C, c
 }
 
 template <typename T>
-__global__ void bn_act_kernel(const T* __restrict__ y, int ldy, const float* __restrict__ scale,
-                              const float* __restrict__ shift, int act, const T* __restrict__ res, int ldr,
-                              T* __restrict__ z, int ldz, int64_t total, int CV, int H, int W, int up2) {
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    int64_t p = idx / CV;
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const T* __restrict__ y, int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
+              int act, const T* __restrict__ res, int ldr, T* __restrict__ z, int ldz, int64_t P, int C, int H,
+              int W, int up2, int CVB, int PL) {
+  const int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
+  const int cv = blockIdx.y * CVB + cvl;
+  if (pl >= PL || cv * 8 >= C) return;
+  f8 sc_, sh;
+  const bool has_bn = scale != nullptr;
+  if (has_bn) {
+    sc_ = load8<float>(scale + cv * 8);
+    sh = load8<float>(shift + cv * 8);
+  }
+  for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
     f8 v = load8<T>(y + p * ldy + cv * 8);
-    if (scale) {
-      f8 sc_ = load8<float>(scale + cv * 8), sh = load8<float>(shift + cv * 8);
+    if (has_bn) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v.v[i] = apply_act(fmaf(v.v[i], sc_.v[i], sh.v[i]), act);
     } else {
@@ -245,11 +265,15 @@ extern "C" int sc_bn_act(const void* y, int ldy, const float* scale, const float
                          const void* residual, int ldr, void* z, int ldz, int N, int H, int W, int C,
                          int upsample2, int dtype, void* stream) {
   if (!y || !z || C % 8 || ldy % 8 || ldz % 8 || (residual && ldr % 8)) return SC_ERR_BAD_ARG;
-  int CV = C / 8;
-  int64_t total = (int64_t)N * H * W * CV;
-  SC_DISPATCH_DTYPE(dtype, (bn_act_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-                               (const T*)y, ldy, scale, shift, act, (const T*)residual, ldr, (T*)z, ldz,
-                               total, CV, H, W, upsample2)));
+  int64_t P = (int64_t)N * H * W;
+  RedGeom g = red_geom(C);
+  int64_t want = (P + g.PL * 4 - 1) / (g.PL * 4);
+  int64_t cap = (kNumSMs * 8) / g.gy;
+  if (cap < 1) cap = 1;
+  dim3 grid((unsigned)(want < cap ? (want < 1 ? 1 : want) : cap), g.gy);
+  SC_DISPATCH_DTYPE(dtype, (bn_act_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)y, ldy, scale, shift, act, (const T*)residual, ldr, (T*)z, ldz, P, C, H, W,
+                               upsample2, g.CVB, g.PL)));
   return check_launch();
 }
 
@@ -284,8 +308,13 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int poo
     f8 sc_ = load8<float>(scale + cv * 8), sh = load8<float>(shift + cv * 8);
     f8 mu = load8<float>(mean + cv * 8), is = load8<float>(invstd + cv * 8);
     double s[8], q[8];
+    float fs[8], fq[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0;
+    for (int i = 0; i < 8; ++i) {
+      s[i] = q[i] = 0.0;
+      fs[i] = fq[i] = 0.f;
+    }
+    int run = 0;
     for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
       f8 yv = load8<T>(y + p * ldy + cv * 8);
       f8 g = load_dz<T>(dz, lddz, pooled, p, cv, H, W);
@@ -293,14 +322,23 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int poo
       for (int i = 0; i < 8; ++i) {
         float gi = g.v[i] * act_mask(fmaf(yv.v[i], sc_.v[i], sh.v[i]), act);
         float xh = (yv.v[i] - mu.v[i]) * is.v[i];
-        s[i] += (double)gi;
-        q[i] += (double)gi * (double)xh;
+        fs[i] += gi;
+        fq[i] = fmaf(gi, xh, fq[i]);
+      }
+      if (++run == 16) {
+        run = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += (double)fs[i];
+          q[i] += (double)fq[i];
+          fs[i] = fq[i] = 0.f;
+        }
       }
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sm[cvl * 8 + i], s[i]);
-      atomicAdd(&sm[CVB * 8 + cvl * 8 + i], q[i]);
+      atomicAdd(&sm[cvl * 8 + i], s[i] + (double)fs[i]);
+      atomicAdd(&sm[CVB * 8 + cvl * 8 + i], q[i] + (double)fq[i]);
     }
   }
   __syncthreads();
@@ -330,53 +368,69 @@ extern "C" int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void
   return check_launch();
 }
 
+// dy = scale*(g - m1 - xhat*m2) with xhat = (y-mean)*invstd  ==  A*g + B*y + D per channel:
+//   A = scale, B = -scale*m2*invstd, D = scale*(m2*mean*invstd - m1).
+// The totals kernel builds the table [A | shift | B | D] once; the apply kernel keeps one channel
+// vector per thread (coefficients in registers) and streams pixels.
 template <typename T>
-__global__ void bn_bwd_apply_kernel(const T* __restrict__ dz, int lddz, int pooled, const T* __restrict__ y,
-                                    int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ gamma, int act, const double* __restrict__ red,
-                                    T* __restrict__ dy, int lddy, float* dgamma, float* dbeta, int64_t total,
-                                    int CV, int C, int H, int W, double invP) {
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    int64_t p = idx / CV;
-    f8 sc_ = load8<float>(scale + cv * 8), sh = load8<float>(shift + cv * 8);
-    f8 mu = load8<float>(mean + cv * 8), is = load8<float>(invstd + cv * 8);
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const T* __restrict__ dz, int lddz, int pooled, const T* __restrict__ y, int ldy,
+                    const float* __restrict__ coef, int act, T* __restrict__ dy, int lddy, int64_t P, int C,
+                    int H, int W, int CVB, int PL) {
+  const int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
+  const int cv = blockIdx.y * CVB + cvl;
+  if (pl >= PL || cv * 8 >= C) return;
+  const f8 cA = load8<float>(coef + cv * 8), cS = load8<float>(coef + C + cv * 8);
+  const f8 cB = load8<float>(coef + 2 * C + cv * 8), cD = load8<float>(coef + 3 * C + cv * 8);
+  for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
     f8 yv = load8<T>(y + p * ldy + cv * 8);
     f8 g = load_dz<T>(dz, lddz, pooled, p, cv, H, W);
     f8 o;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      int c = cv * 8 + i;
-      float gi = g.v[i] * act_mask(fmaf(yv.v[i], sc_.v[i], sh.v[i]), act);
-      float xh = (yv.v[i] - mu.v[i]) * is.v[i];
-      float m1 = (float)(red[c] * invP), m2 = (float)(red[C + c] * invP);
-      // gamma*invstd == scale
-      o.v[i] = sc_.v[i] * (gi - m1 - xh * m2);
+      float gi = g.v[i] * act_mask(fmaf(yv.v[i], cA.v[i], cS.v[i]), act);
+      o.v[i] = fmaf(cA.v[i], gi, fmaf(cB.v[i], yv.v[i], cD.v[i]));
     }
     store8<T>(dy + p * lddy + cv * 8, o);
   }
 }
 
-// totals row = sum of the partial rows; also the parameter gradients dbeta = sum g, dgamma = sum g*xhat
-__global__ void bn_bwd_totals_kernel(double* __restrict__ partials, int nrows, int C, float* dgamma, float* dbeta) {
-  __shared__ double sh[8][33];
+// totals row = sum of the partial rows; the parameter gradients dbeta = sum g, dgamma = sum g*xhat;
+// and the apply kernel's coefficient table
+__global__ void bn_bwd_totals_kernel(double* __restrict__ partials, int nrows, int C, double invP,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd,
+                                     float* dgamma, float* dbeta, float* __restrict__ coef) {
+  __shared__ double sh[2][8][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int i = blockIdx.x * 32 + tx;
-  double s = 0.0;
-  if (i < 2 * C)
-    for (int r = ty; r < nrows; r += 8) s += partials[(int64_t)r * 2 * C + i];
-  sh[ty][tx] = s;
+  const int c = blockIdx.x * 32 + tx;
+  double s1 = 0.0, s2 = 0.0;
+  if (c < C)
+    for (int r = ty; r < nrows; r += 8) {
+      s1 += partials[(int64_t)r * 2 * C + c];
+      s2 += partials[(int64_t)r * 2 * C + C + c];
+    }
+  sh[0][ty][tx] = s1;
+  sh[1][ty][tx] = s2;
   __syncthreads();
-  if (ty != 0 || i >= 2 * C) return;
+  if (ty != 0 || c >= C) return;
 #pragma unroll
-  for (int j = 1; j < 8; ++j) s += sh[j][tx];
-  partials[(int64_t)nrows * 2 * C + i] = s;
-  if (dgamma) {
-    if (i < C) dbeta[i] += (float)s;
-    else dgamma[i - C] += (float)s;
+  for (int j = 1; j < 8; ++j) {
+    s1 += sh[0][j][tx];
+    s2 += sh[1][j][tx];
   }
+  partials[(int64_t)nrows * 2 * C + c] = s1;
+  partials[(int64_t)nrows * 2 * C + C + c] = s2;
+  if (dgamma) {
+    dbeta[c] += (float)s1;
+    dgamma[c] += (float)s2;
+  }
+  const float m1 = (float)(s1 * invP), m2 = (float)(s2 * invP);
+  const float sc_ = scale[c], is = invstd[c], mu = mean[c];
+  coef[c] = sc_;
+  coef[C + c] = shift[c];
+  coef[2 * C + c] = -sc_ * m2 * is;
+  coef[3 * C + c] = sc_ * (m2 * mu * is - m1);
 }
 
 extern "C" int sc_bn_bwd_apply(const void* dz, int lddz, int pooled, const void* y, int ldy,
@@ -388,13 +442,19 @@ extern "C" int sc_bn_bwd_apply(const void* dz, int lddz, int pooled, const void*
       lddy % 8)
     return SC_ERR_BAD_ARG;
   (void)gamma;
-  int CV = C / 8;
-  int64_t P = (int64_t)N * H * W, total = P * CV;
-  bn_bwd_totals_kernel<<<(2 * C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(partials, nrows, C, dgamma, dbeta);
-  const double* red = partials + (int64_t)nrows * 2 * C;
-  SC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
-                               (const T*)dz, lddz, pooled, (const T*)y, ldy, scale, shift, mean, invstd, gamma,
-                               act, red, (T*)dy, lddy, dgamma, dbeta, total, CV, C, H, W, 1.0 / (double)P)));
+  int64_t P = (int64_t)N * H * W;
+  // the coefficient table lives right after the totals row of the partials buffer (4*C floats = 2*C doubles)
+  float* coef = reinterpret_cast<float*>(partials + ((int64_t)nrows + 1) * 2 * C);
+  bn_bwd_totals_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+      partials, nrows, C, 1.0 / (double)P, scale, shift, mean, invstd, dgamma, dbeta, coef);
+  RedGeom g = red_geom(C);
+  int64_t want = (P + g.PL * 4 - 1) / (g.PL * 4);
+  int64_t cap = (kNumSMs * 8) / g.gy;
+  if (cap < 1) cap = 1;
+  dim3 grid((unsigned)(want < cap ? (want < 1 ? 1 : want) : cap), g.gy);
+  SC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                               (const T*)dz, lddz, pooled, (const T*)y, ldy, coef, act, (T*)dy, lddy, P, C, H, W,
+                               g.CVB, g.PL)));
   return check_launch();
 }
 
@@ -709,6 +769,35 @@ extern "C" int sc_adam_step(float* p, const float* g, float* m, float* v, int64_
   float bc2 = 1.f - powf(beta2, (float)step_host);
   adam_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1,
                                                                sqrtf(bc2), grad_scale);
+  return check_launch();
+}
+
+// device-resident step counter and learning rate: the whole train step can be replayed as a CUDA graph
+__global__ void adam_step_inc_kernel(int* step) { *step += 1; }
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, const float* __restrict__ lr_dev, float b1, float b2,
+                                float eps, const int* __restrict__ step_dev, float gs) {
+  const double t = (double)*step_dev;
+  const float bc1 = (float)(1.0 - pow((double)b1, t));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
+  const float step_size = *lr_dev / bc1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * gs;
+    float mi = m[i] + (gi - m[i]) * (1.f - b1);
+    float vi = v[i] * b2 + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] - step_size * (mi / denom);
+  }
+}
+
+extern "C" int sc_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev,
+                                float beta1, float beta2, float eps, int* step_dev, float grad_scale, void* stream) {
+  if (!p || !g || !m || !v || !lr_dev || !step_dev || n <= 0) return SC_ERR_BAD_ARG;
+  adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  adam_dev_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps, step_dev,
+                                                                   grad_scale);
   return check_launch();
 }
 

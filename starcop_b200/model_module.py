@@ -211,14 +211,25 @@ class HyperStarcopUnet(UnetParameters):
 
     # ---- fused optimiser (Adam on the flat arena) -----------------------------------------------
     def adam_step(self, lr, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        """torch.optim.Adam update of the flat arena.  Step counter and learning rate live on the
+        device (sc_adam_step_dev) so the call can sit inside a captured CUDA graph."""
         self._materialize()
         p, g = self._flat
         if self._adam_state is None:
-            self._adam_state = [torch.zeros_like(p), torch.zeros_like(p), 0]
-        m, v, _ = self._adam_state
-        self._adam_state[2] += 1
-        _lib.call("sc_adam_step", p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), lr,
-                  betas[0], betas[1], eps, self._adam_state[2], grad_scale, _stream(p.device))
+            self._adam_state = {"m": torch.zeros_like(p), "v": torch.zeros_like(p),
+                                "step": torch.zeros(1, dtype=torch.int32, device=p.device),
+                                "lr": torch.full((1,), float(lr), dtype=torch.float32, device=p.device), "lr_host": float(lr)}
+        st = self._adam_state
+        if st["lr_host"] != float(lr) and not torch.cuda.is_current_stream_capturing():
+            st["lr"].fill_(float(lr))
+            st["lr_host"] = float(lr)
+        _lib.call("sc_adam_step_dev", p.data_ptr(), g.data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(), p.numel(),
+                  st["lr"].data_ptr(), betas[0], betas[1], eps, st["step"].data_ptr(), grad_scale, _stream(p.device))
+
+    def set_lr(self, lr):
+        if self._adam_state is not None:
+            self._adam_state["lr"].fill_(float(lr))
+            self._adam_state["lr_host"] = float(lr)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -382,6 +393,13 @@ class ModelModule(_Base):
             except Exception as e:                         # noqa: BLE001
                 print(f"Bug logging {e}")
 
+    def _pw(self):
+        """pos_weight as a Python float without a device sync on the hot path (cached per tensor version)."""
+        key = (self.pos_weight.data_ptr(), self.pos_weight._version)
+        if getattr(self, "_pw_cache", (None, None))[0] != key:
+            self._pw_cache = (key, float(self.pos_weight))
+        return self._pw_cache[1]
+
     # ---- hot path -----------------------------------------------------------------------------------
     def forward(self, x):
         """model_module.py:90-98: network(normalizer.normalize_x(x)); the normalisation is fused
@@ -418,7 +436,7 @@ class ModelModule(_Base):
             cm = torch.zeros(4, dtype=torch.long, device=dev)
             cnt = torch.zeros(B, dtype=torch.long, device=dev)
             _lib.call("sc_bce_fused", logits.data_ptr(), y.data_ptr(), w.data_ptr() if w is not None else 0,
-                      float(self.pos_weight), B, HW, 0.0, loss_sum.data_ptr(), 0, cm.data_ptr(), cnt.data_ptr(),
+                      self._pw(), B, HW, 0.0, loss_sum.data_ptr(), 0, cm.data_ptr(), cnt.data_ptr(),
                       0, 0, 0, 0, 0, 0, 0, _stream(dev))
             loss = (loss_sum / logits.numel()).float()[0]
             self.log(f"{prefix}_loss", loss, on_epoch=True)
@@ -485,7 +503,7 @@ class ModelModule(_Base):
             w = batch["weight_loss"].contiguous().float() if weighted else None
             cnt = torch.zeros(B, dtype=torch.long, device=dev)
             _lib.call("sc_bce_fused", logits.data_ptr(), y.data_ptr(), w.data_ptr() if weighted else 0,
-                      float(self.pos_weight), B, H * W, 0.0, 0, 0, 0, 0, 0, cnt.data_ptr(), pred.data_ptr(),
+                      self._pw(), B, H * W, 0.0, 0, 0, 0, 0, 0, cnt.data_ptr(), pred.data_ptr(),
                       lpx.data_ptr() if weighted else 0, lpw.data_ptr() if weighted else 0, pb.data_ptr(),
                       diff.data_ptr(), _stream(dev))
             batch["prediction"] = pred
@@ -515,7 +533,7 @@ class ModelModule(_Base):
         loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
         grad = torch.empty_like(logits)
         _lib.call("sc_bce_fused", logits.data_ptr(), y.contiguous().float().data_ptr(),
-                  w.contiguous().float().data_ptr() if w is not None else 0, float(self.pos_weight), B, n // B,
+                  w.contiguous().float().data_ptr() if w is not None else 0, self._pw(), B, n // B,
                   1.0 / n, loss_sum.data_ptr(), grad.data_ptr(), 0, 0, 0, 0, 0, 0, 0, 0, 0, _stream(dev))
         net._backward_impl(grad)
         scale = 1.0
@@ -523,3 +541,33 @@ class ModelModule(_Base):
             scale = grad_sync(net.flat_grads)
         net.adam_step(self.lr if lr is None else lr, grad_scale=scale)
         return (loss_sum / n).float()[0]
+
+    def make_graphed_train_step(self, example_batch, grad_sync=None, warmup=2):
+        assert warmup >= 1, "at least one eager step must run first (it sizes the arenas and caches host state)"
+        """Capture train_step_fused into ONE CUDA graph (every buffer of the step comes from the static
+        arenas, the Adam step counter and lr are device resident).  Returns ``step(batch) -> loss``:
+        the batch is copied into the graph's static input buffers, the graph is replayed (~600 kernel
+        launches, one cudaGraphLaunch), the returned loss tensor is the graph's static output."""
+        dev = example_batch["input"].device
+        keys = ["input", "output"] + (["weight_loss"] if self.reduction == "none" else [])
+        static = {k: torch.empty_like(example_batch[k], device=dev) for k in keys}
+        for k in keys:
+            static[k].copy_(example_batch[k])
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # sizes the arenas, JITs nothing, warms NCCL
+                self.train_step_fused(static, grad_sync=grad_sync)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self.train_step_fused(static, grad_sync=grad_sync)
+
+        def step(batch):
+            for k in keys:
+                static[k].copy_(batch[k], non_blocking=True)
+            graph.replay()
+            return loss
+        step.graph, step.static = graph, static
+        return step

@@ -194,3 +194,22 @@ def test_requires_cuda_and_divisible_by_32():
         model(torch.zeros(1, 4, 48, 64, device=DEV))
     with pytest.raises(Exception):
         model(torch.zeros(1, 4, 64, 64))           # CPU tensor: no CPU path
+
+
+def test_graphed_train_step_matches_eager():
+    """The CUDA-graph replay of the fused step is the same computation as launching it eagerly."""
+    _, m1 = build_pair(1.0)
+    _, m2 = build_pair(1.0)
+    m1.train(); m2.train()
+    b0 = to_dev(synthetic.hyperstarcop_batch(2, size=64, seed=20))
+    m1.train_step_fused(b0)                                  # the graph builder runs one eager warm-up step
+    step = m2.make_graphed_train_step(b0, warmup=1)
+    for s in range(3):
+        b = to_dev(synthetic.hyperstarcop_batch(2, size=64, seed=20 + s))
+        l1 = m1.train_step_fused(b)
+        l2 = step(b)
+        # step 0 starts from identical weights; afterwards fp32-atomic summation order in the weight
+        # gradients + Adam's sign-like first updates let the two runs drift by ~1e-4 (see the Adam test)
+        assert abs(l1.item() - l2.item()) <= (1e-6 if s == 0 else 2e-3) * abs(l1.item()), (s, l1.item(), l2.item())
+    assert (m1.network.flat_params - m2.network.flat_params).abs().mean().item() < 1e-4
+    assert int(m2.network._adam_state["step"].item()) == 4   # one eager warm-up + 3 replays (capture records, it does not execute)
