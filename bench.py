@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
+    ap.add_argument("--profile", action="store_true",
+                    help="profiling run (under ncu): 1 warm-up, no e2e loop, no roofline probe; prints no bench line")
     return ap.parse_args()
 
 
@@ -197,6 +199,9 @@ def main():
             ms = t.item()
         return ms, _lib.launch_count() - c0
 
+    if args.profile:
+        timed(step_resident, args.steps, 1)
+        return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()

@@ -169,6 +169,20 @@ int sc_ratio_product(const float* bg, const float* sig, float* out, int T, int64
                      float percentile, float zero_value, void* workspace, void* stream);
 int sc_weight_mag1c(const float* mag1c, float* out, int64_t n, void* stream);
 
+/* ---- A12: MLR band reconstruction (starcop/data/feature_extration.py:58-124, sklearn
+ * LinearRegression with intercept): bands (T,K,HW) f32, target (T,HW) -> recon (T,HW) = X.coef + b,
+ * normal equations of the centred data in fp64.  K <= 9.  The ratio itself is then
+ * sc_ratio_product(bg = target, sig = recon, zero_value = -0.5) + sc_zero_override(target). */
+int64_t sc_mlr_workspace_bytes(int T);
+int sc_mlr_reconstruct(const float* bands, const float* target, float* recon, int T, int K, int64_t HW,
+                       void* workspace, void* stream);
+/* out[i] = value where ref[i] == 0 (np.where(band_target_signal == 0.0, zero_value_out, R), :111) */
+int sc_zero_override(const float* ref, float* out, int64_t n, float value, void* stream);
+
+/* ---- A17: EMIT input rescale (starcop/emit_tools/emit_dataset.py:62-101): magic (H,W), rgb (3,H,W)
+ * -> out (4, H//32*32, W//32*32) = [clip(mf/240,0,2)*1750, clip(rgb/20,0,2)*60], nan_to_num */
+int sc_emit_rescale(const float* magic, const float* rgb, float* out, int H, int W, void* stream);
+
 /* ---- A14: binary opening with the 3x3 cross (starcop/baselines.py:25-27, 54-58) ------------- */
 int sc_threshold_opening(const float* pred, float threshold, int64_t* out, uint8_t* scratch,
                          int B, int H, int W, void* stream);

@@ -10,8 +10,8 @@ rows = list(csv.DictReader(lines))
 def us(r):
     v = float(r['Metric Value'].replace(',', '')); u = r['Metric Unit']
     return v / 1e3 if u == 'ns' else (v * 1e3 if u == 'ms' else v)
-adam = [i for i, r in enumerate(rows) if r['Kernel Name'].startswith('adam_kernel')]
-s, e = adam[2] + 1, adam[3] + 1            # 4th step = the timed resident step
+adam = [i for i, r in enumerate(rows) if r['Kernel Name'].startswith(('adam_kernel', 'adam_dev_kernel'))]
+s, e = adam[-2] + 1, adam[-1] + 1          # the last complete step
 step = rows[s:e]
 tot = sum(us(r) for r in step)
 print(f"launches in step: {len(step)}   sum of kernel time: {tot/1e3:.2f} ms")

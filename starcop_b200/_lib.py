@@ -43,6 +43,10 @@ SIGNATURES = {
     "sc_ratio_workspace_bytes": [I, L],
     "sc_ratio_product": [P, P, P, I, L, F, F, P, P],
     "sc_weight_mag1c": [P, P, L, P],
+    "sc_mlr_workspace_bytes": [I],
+    "sc_mlr_reconstruct": [P, P, P, I, I, L, P, P],
+    "sc_zero_override": [P, P, L, F, P],
+    "sc_emit_rescale": [P, P, P, I, I, P],
     "sc_threshold_opening": [P, F, P, P, I, I, I, P],
     "sc_tc_supported": [],
     "sc_tc_pack_weights": [P, P, I, I, I, I, I, I, I, P],
@@ -50,7 +54,7 @@ SIGNATURES = {
     "sc_tc_conv_fprop": [P, I, P, P, I, P, P, I, I, I, I, I, I, I, I, I, P],
     "sc_tc_conv_wgrad": [P, I, P, I, P, I, I, I, I, I, I, I, I, P],
 }
-_RESTYPES = {"sc_last_cuda_error": ctypes.c_char_p, "sc_mag1c_smem_bytes": c_int64, "sc_bn_partials_bytes": c_int64, "sc_dwconv_wgrad_workspace_bytes": c_int64,
+_RESTYPES = {"sc_last_cuda_error": ctypes.c_char_p, "sc_mag1c_smem_bytes": c_int64, "sc_bn_partials_bytes": c_int64, "sc_mlr_workspace_bytes": c_int64, "sc_dwconv_wgrad_workspace_bytes": c_int64,
              "sc_ratio_workspace_bytes": c_int64}
 
 _lib = None

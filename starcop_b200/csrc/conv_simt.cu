@@ -326,50 +326,71 @@ __device__ __forceinline__ void stage_dw_weights(float* ws, const float* __restr
   __syncthreads();
 }
 
-template <typename T>
-__global__ void __launch_bounds__(256)
+// Each thread produces a strip of 4 horizontally adjacent outputs of one 8-channel vector: the
+// 3 x (3*stride+3) input window is loaded (and normalised) once instead of 9 loads per output.
+template <typename T, int STRIDE, int TW>
+__global__ void __launch_bounds__(256, (TW == 2 ? 3 : 1))
 dwconv_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
                     const float* __restrict__ shift, int act, const float* __restrict__ w,
-                    T* __restrict__ y, int ldy, int N, int H, int W, int C, int stride, int Ho, int Wo) {
+                    T* __restrict__ y, int ldy, int N, int H, int W, int C, int Ho, int Wo) {
   extern __shared__ float ws[];   // [9][C]
   stage_dw_weights(ws, w, C);
-  int CV = C / 8;
-  int64_t total = (int64_t)N * Ho * Wo * CV;
+  constexpr int NI = (TW - 1) * STRIDE + 3;
+  const int CV = C / 8, WS = (Wo + TW - 1) / TW;
+  const int64_t total = (int64_t)N * Ho * WS * CV;
   const bool has_bn = scale != nullptr;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    int64_t p = idx / CV;
-    int wo = (int)(p % Wo);
-    int64_t t = p / Wo;
-    int ho = (int)(t % Ho);
-    int n = (int)(t / Ho);
+    const int cv = (int)(idx % CV);
+    int64_t t = idx / CV;
+    const int wo0 = (int)(t % WS) * TW;
+    t /= WS;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
     f8 sc_, sh;
     if (has_bn) {
       sc_ = load8<float>(scale + cv * 8);
       sh = load8<float>(shift + cv * 8);
     }
-    float acc[8];
+    float acc[TW][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int j = 0; j < TW; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+    const int iw0 = wo0 * STRIDE - 1;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
-      int ih = ho * stride - 1 + kh;
+      const int ih = ho * STRIDE - 1 + kh;
       if (ih < 0 || ih >= H) continue;
+      const T* xr = x + (((int64_t)n * H + ih) * W) * ldx + cv * 8;
+      f8 in[NI];
+#pragma unroll
+      for (int c = 0; c < NI; ++c) {
+        const int iw = iw0 + c;
+        if (iw >= 0 && iw < W) {
+          in[c] = load_bnact<T>(xr + (int64_t)iw * ldx, sc_, sh, has_bn, act);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) in[c].v[i] = 0.f;
+        }
+      }
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        int iw = wo * stride - 1 + kw;
-        if (iw < 0 || iw >= W) continue;
-        f8 v = load_bnact<T>(x + (((int64_t)n * H + ih) * W + iw) * ldx + cv * 8, sc_, sh, has_bn, act);
-        f8 wv = load8<float>(ws + (kh * 3 + kw) * C + cv * 8);
+        const f8 wv = load8<float>(ws + (kh * 3 + kw) * C + cv * 8);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(v.v[i], wv.v[i], acc[i]);
+        for (int j = 0; j < TW; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(in[j * STRIDE + kw].v[i], wv.v[i], acc[j][i]);
       }
     }
-    f8 o;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o.v[i] = acc[i];
-    store8<T>(y + p * ldy + cv * 8, o);
+    for (int j = 0; j < TW; ++j) {
+      if (wo0 + j >= Wo) break;
+      f8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = acc[j][i];
+      store8<T>(y + ((((int64_t)n * Ho + ho) * Wo) + wo0 + j) * ldy + cv * 8, o);
+    }
   }
 }
 
@@ -384,10 +405,18 @@ extern "C" int sc_dwconv_fprop(const void* x, int ldx, const float* scale, const
                                void* stream) {
   if (!x || !w || !y || C % 8 || ldx % 8 || ldy % 8 || (stride != 1 && stride != 2) || C > 1280) return SC_ERR_BAD_ARG;
   int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  int64_t total = (int64_t)N * Ho * Wo * (C / 8);
+  // measured on B200 (profiles/): stride 1 is fastest with 4-wide strips, stride 2 with 2-wide strips
+  // at 3 blocks per SM (these kernels are latency bound: occupancy vs. reuse)
+  const int tw = stride == 1 ? 4 : 2;
+  int64_t total = (int64_t)N * Ho * ((Wo + tw - 1) / tw) * (C / 8);
   size_t smem = (size_t)9 * C * sizeof(float);
-  SC_DISPATCH_DTYPE(dtype, (dwconv_fprop_kernel<T><<<ew_blocks2(total), 256, smem, (cudaStream_t)stream>>>(
-                               (const T*)x, ldx, scale, shift, act, w, (T*)y, ldy, N, H, W, C, stride, Ho, Wo)));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stride == 1)
+    SC_DISPATCH_DTYPE(dtype, (dwconv_fprop_kernel<T, 1, 4><<<ew_blocks2(total), 256, smem, st>>>(
+                                 (const T*)x, ldx, scale, shift, act, w, (T*)y, ldy, N, H, W, C, Ho, Wo)));
+  else
+    SC_DISPATCH_DTYPE(dtype, (dwconv_fprop_kernel<T, 2, 2><<<ew_blocks2(total), 256, smem, st>>>(
+                                 (const T*)x, ldx, scale, shift, act, w, (T*)y, ldy, N, H, W, C, Ho, Wo)));
   return check_launch();
 }
 
@@ -436,12 +465,78 @@ dwconv_dgrad_kernel(const T* __restrict__ dy, int lddy, const float* __restrict_
   }
 }
 
+// stride-1 data gradient = depthwise correlation of dy with the mirrored filter: same 4-wide strips
+template <typename T>
+__global__ void __launch_bounds__(256)
+dwconv_dgrad_s1_kernel(const T* __restrict__ dy, int lddy, const float* __restrict__ w, T* __restrict__ dx, int lddx,
+                       int N, int H, int W, int C) {
+  extern __shared__ float ws[];
+  stage_dw_weights(ws, w, C);
+  constexpr int TW = 4, NI = TW + 2;
+  const int CV = C / 8, WS = (W + TW - 1) / TW;
+  const int64_t total = (int64_t)N * H * WS * CV;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % CV);
+    int64_t t = idx / CV;
+    const int iw0 = (int)(t % WS) * TW;
+    t /= WS;
+    const int ih = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[TW][8];
+#pragma unroll
+    for (int j = 0; j < TW; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int oh = ih + 1 - kh;                 // dx[ih] += dy[ih+1-kh] * w[kh]
+      if (oh < 0 || oh >= H) continue;
+      const T* gr = dy + (((int64_t)n * H + oh) * W) * lddy + cv * 8;
+      f8 in[NI];
+#pragma unroll
+      for (int c = 0; c < NI; ++c) {
+        const int ow = iw0 - 1 + c;
+        if (ow >= 0 && ow < W) {
+          in[c] = load8<T>(gr + (int64_t)ow * lddy);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) in[c].v[i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const f8 wv = load8<float>(ws + (kh * 3 + kw) * C + cv * 8);
+        // dx[iw0+j] += dy[iw0+j+1-kw] * w[kw]  ->  in[j + 2 - kw]
+#pragma unroll
+        for (int j = 0; j < TW; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(in[j + 2 - kw].v[i], wv.v[i], acc[j][i]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < TW; ++j) {
+      if (iw0 + j >= W) break;
+      f8 o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = acc[j][i];
+      store8<T>(dx + ((((int64_t)n * H + ih) * W) + iw0 + j) * lddx + cv * 8, o);
+    }
+  }
+}
+
 extern "C" int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* dx, int lddx, int N, int H, int W,
                                int C, int stride, int dtype, void* stream) {
   if (!dy || !w || !dx || C % 8 || lddy % 8 || lddx % 8 || (stride != 1 && stride != 2) || C > 1280) return SC_ERR_BAD_ARG;
   int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
   int64_t total = (int64_t)N * H * W * (C / 8);
   size_t smem = (size_t)9 * C * sizeof(float);
+  if (stride == 1) {
+    int64_t strips = (int64_t)N * H * ((W + 3) / 4) * (C / 8);
+    SC_DISPATCH_DTYPE(dtype, (dwconv_dgrad_s1_kernel<T><<<ew_blocks2(strips), 256, smem, (cudaStream_t)stream>>>(
+                                 (const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C)));
+    return check_launch();
+  }
   SC_DISPATCH_DTYPE(dtype, (dwconv_dgrad_kernel<T><<<ew_blocks2(total), 256, smem, (cudaStream_t)stream>>>(
                                (const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C, stride, Ho, Wo)));
   return check_launch();

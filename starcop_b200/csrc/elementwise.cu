@@ -86,11 +86,13 @@ static int red_blocks(int64_t P, int PL, int gy) {
 template <typename T>
 __global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __restrict__ partials, int64_t P,
                                 int C, int CVB, int PL) {
-  extern __shared__ double sm[];   // [2][CVB*8]
+  extern __shared__ double sm[];   // [PL][CVB][16]
   int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
   int cv = blockIdx.y * CVB + cvl;
-  for (int i = threadIdx.x; i < 2 * CVB * 8; i += blockDim.x) sm[i] = 0.0;
-  __syncthreads();
+  if (pl < PL && cv * 8 >= C) {
+    double* mine = sm + ((size_t)pl * CVB + cvl) * 16;
+    for (int i = 0; i < 16; ++i) mine[i] = 0.0;
+  }
   if (pl < PL && cv * 8 < C) {
     // fp32 partial sums over runs of 16 pixels, flushed into fp64 accumulators (keeps the fp64 pipe idle)
     double s[8], q[8];
@@ -118,20 +120,24 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __rest
         }
       }
     }
+    // stage this thread's 16 partials: sm[pl][cvl][16] (no shared-memory atomics: with few channels
+    // hundreds of threads would contend on a handful of fp64 CAS loops)
+    double* mine = sm + ((size_t)pl * CVB + cvl) * 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sm[cvl * 8 + i], s[i] + (double)fs[i]);
-      atomicAdd(&sm[CVB * 8 + cvl * 8 + i], q[i] + (double)fq[i]);
+      mine[i] = s[i] + (double)fs[i];
+      mine[8 + i] = q[i] + (double)fq[i];
     }
   }
   __syncthreads();
   double* row = partials + (int64_t)blockIdx.x * 2 * C;
-  for (int i = threadIdx.x; i < CVB * 8; i += blockDim.x) {
-    int c = blockIdx.y * CVB * 8 + i;
-    if (c < C) {
-      row[c] = sm[i];
-      row[C + c] = sm[CVB * 8 + i];
-    }
+  for (int o = threadIdx.x; o < CVB * 16; o += blockDim.x) {
+    const int cvo = o / 16, k = o % 16;          // k < 8: sum, k >= 8: second moment
+    const int c = (blockIdx.y * CVB + cvo) * 8 + (k & 7);
+    if (c >= C) continue;
+    double t = 0.0;
+    for (int j = 0; j < PL; ++j) t += sm[((size_t)j * CVB + cvo) * 16 + k];
+    row[(k < 8 ? 0 : C) + c] = t;
   }
 }
 
@@ -143,7 +149,7 @@ extern "C" int sc_bn_stats(const void* y, int ldy, double* partials, int* nrows_
   RedGeom g = red_geom(C);
   dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
   *nrows_host = (int)grid.x;
-  size_t smem = 2 * g.CVB * 8 * sizeof(double);
+  size_t smem = (size_t)g.PL * g.CVB * 16 * sizeof(double);   // <= 32 KB
   SC_DISPATCH_DTYPE(dtype, (bn_stats_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
                                (const T*)y, ldy, partials, P, C, g.CVB, g.PL)));
   return check_launch();
@@ -299,11 +305,13 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int poo
                                      int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, int act,
                                      double* __restrict__ partials, int64_t P, int C, int H, int W, int CVB, int PL) {
-  extern __shared__ double sm[];
+  extern __shared__ double sm[];   // [PL][CVB][16]
   int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
   int cv = blockIdx.y * CVB + cvl;
-  for (int i = threadIdx.x; i < 2 * CVB * 8; i += blockDim.x) sm[i] = 0.0;
-  __syncthreads();
+  if (pl < PL && cv * 8 >= C) {
+    double* mine = sm + ((size_t)pl * CVB + cvl) * 16;
+    for (int i = 0; i < 16; ++i) mine[i] = 0.0;
+  }
   if (pl < PL && cv * 8 < C) {
     f8 sc_ = load8<float>(scale + cv * 8), sh = load8<float>(shift + cv * 8);
     f8 mu = load8<float>(mean + cv * 8), is = load8<float>(invstd + cv * 8);
@@ -335,20 +343,24 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int poo
         }
       }
     }
+    // stage this thread's 16 partials: sm[pl][cvl][16] (no shared-memory atomics: with few channels
+    // hundreds of threads would contend on a handful of fp64 CAS loops)
+    double* mine = sm + ((size_t)pl * CVB + cvl) * 16;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      atomicAdd(&sm[cvl * 8 + i], s[i] + (double)fs[i]);
-      atomicAdd(&sm[CVB * 8 + cvl * 8 + i], q[i] + (double)fq[i]);
+      mine[i] = s[i] + (double)fs[i];
+      mine[8 + i] = q[i] + (double)fq[i];
     }
   }
   __syncthreads();
   double* row = partials + (int64_t)blockIdx.x * 2 * C;
-  for (int i = threadIdx.x; i < CVB * 8; i += blockDim.x) {
-    int c = blockIdx.y * CVB * 8 + i;
-    if (c < C) {
-      row[c] = sm[i];
-      row[C + c] = sm[CVB * 8 + i];
-    }
+  for (int o = threadIdx.x; o < CVB * 16; o += blockDim.x) {
+    const int cvo = o / 16, k = o % 16;          // k < 8: sum, k >= 8: second moment
+    const int c = (blockIdx.y * CVB + cvo) * 8 + (k & 7);
+    if (c >= C) continue;
+    double t = 0.0;
+    for (int j = 0; j < PL; ++j) t += sm[((size_t)j * CVB + cvo) * 16 + k];
+    row[(k < 8 ? 0 : C) + c] = t;
   }
 }
 
@@ -361,7 +373,7 @@ extern "C" int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void
   RedGeom g = red_geom(C);
   dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
   *nrows_host = (int)grid.x;
-  size_t smem = 2 * g.CVB * 8 * sizeof(double);
+  size_t smem = (size_t)g.PL * g.CVB * 16 * sizeof(double);   // <= 32 KB
   SC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
                                (const T*)dz, lddz, pooled, (const T*)y, ldy, scale, shift, mean, invstd, act,
                                red, P, C, H, W, g.CVB, g.PL)));

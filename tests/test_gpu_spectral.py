@@ -90,3 +90,27 @@ def test_ratio_product_batched_tiles_vs_oracle():
     ok = (b > 1e-3)
     c_gpu = np.median(((r[0] * (b + 1e-6) + b) / s)[ok])
     assert abs(c_gpu - c) <= 1e-5 * abs(c)
+
+
+def test_mlr_ratio_vs_reference(golden):
+    g = golden("features.npz")
+    bands = torch.from_numpy(g["mlr_bands"]).to(DEV)
+    tgt = torch.from_numpy(g["mlr_target"]).to(DEV)
+    r = features.ratio_MLR_local(bands, tgt).cpu().numpy()
+    ref = g["mlr_ratio"]
+    assert np.array_equal(r == np.float32(-0.5), ref == np.float32(-0.5))     # nodata / zero-target mask
+    assert np.allclose(r, ref, rtol=1e-3, atol=2e-4)
+    r5 = features.ratio_MLR_local_5IN(*[b for b in bands], tgt).cpu().numpy()
+    assert np.array_equal(r5, r)
+
+
+def test_emit_rescale_vs_oracle():
+    rng = np.random.default_rng(0)
+    magic = rng.exponential(120, (70, 100)).astype(np.float32)
+    rgb = rng.uniform(0, 50, (3, 70, 100)).astype(np.float32)
+    magic[3, 4] = np.nan
+    rgb[1, 5, 6] = np.nan
+    out = features.emit_rescale(torch.from_numpy(magic).to(DEV), torch.from_numpy(rgb).to(DEV)).cpu().numpy()
+    ref = ofeat.emit_rescale(magic, rgb)
+    assert out.shape == ref.shape == (4, 64, 96)
+    assert np.array_equal(out, ref)

@@ -213,3 +213,35 @@ def test_graphed_train_step_matches_eager():
         assert abs(l1.item() - l2.item()) <= (1e-6 if s == 0 else 2e-3) * abs(l1.item()), (s, l1.item(), l2.item())
     assert (m1.network.flat_params - m2.network.flat_params).abs().mean().item() < 1e-4
     assert int(m2.network._adam_state["step"].item()) == 4   # one eager warm-up + 3 replays (capture records, it does not execute)
+
+
+def test_per_tile_validation_and_padded_predict():
+    from oracle import loss_metrics as olm
+    from starcop_b200 import tiling, validation
+    oracle, model = build_pair(1.0)
+    oracle.eval(); model.eval()
+    tiles = [synthetic.hyperstarcop_batch(1, size=64, seed=40 + i) for i in range(3)]
+    rows, gcm, sweep = validation.run_validation(model, tiles)
+    assert len(rows) == 3 and len(sweep) == 16
+    tot = torch.zeros(2, 2, dtype=torch.long)
+    for t, row in zip(tiles, rows):
+        with torch.no_grad():
+            bo = oracle.batch_with_preds(t)
+        safe = bo["logits"].abs() > 1e-3
+        cm_o = olm.confusion_matrix(bo["pred_binary"], bo["output_norm"].long())
+        if bool(safe.all()):
+            assert row["TP"] == int(cm_o[1, 1]) and row["FP"] == int(cm_o[0, 1])
+        assert row["label_pixels_plume"] == int(t["output"].sum())
+        assert row["pred_classification"] == int(bo["pred_classification"][0, 0])
+        tot += cm_o
+    assert int(gcm.sum()) == 3 * 64 * 64
+    # whole-scene prediction with reflect padding to a multiple of 32 (padding.py semantics)
+    scene = synthetic.hyperstarcop_batch(1, size=96, seed=7)["input"][0][:, :70, :90]
+    pred = tiling.padded_predict(scene.numpy(), model)
+    assert pred.shape == (1, 70, 90)
+    from oracle.tiling import find_padding
+    pr, pc = find_padding(70, 32), find_padding(90, 32)
+    padded = torch.nn.functional.pad(scene[None], (pc[0], pc[1], pr[0], pr[1]), mode="reflect")
+    with torch.no_grad():
+        ref = oracle(padded)[0][:, pr[0]:pr[0] + 70, pc[0]:pc[0] + 90]
+    assert np.abs(pred - ref.numpy()).max() <= 1e-3

@@ -70,3 +70,17 @@ def test_synthetic_batch_contract():
     assert b["output"].shape == (4, 1, 64, 64) and set(b["output"].unique().tolist()) <= {0.0, 1.0}
     assert b["weight_loss"].min() >= 0.1 and b["weight_loss"].max() <= 1.0
     assert b["has_plume"].dtype == torch.int64 and len(b["id"]) == 4
+
+
+def test_tiling_matches_oracle_and_notebook_counts():
+    from oracle import tiling as ot
+    from starcop_b200 import tiling
+    for args in (((512, 512), (128, 128), (64, 64)), ((512, 512), (512, 512), (0, 0)), ((300, 500), (128, 128), (32, 64))):
+        assert tiling.create_windows(*args) == ot.create_windows(*args)
+    wins = tiling.create_windows((512, 512), (128, 128), (64, 64))
+    assert len(wins) == 49                                     # 441 chips / 9 tiles in the reference notebook
+    assert tiling.tile_id("x", wins[1]) == ot.tile_id("x", wins[1]) == "x_r0_c64_w128_h128"
+    lab = np.zeros((128, 128), np.float32); lab[:5, :8] = 1
+    assert tiling.has_plume(torch.from_numpy(lab)) == ot.has_plume(lab) == False
+    for v in (1242, 1280, 70, 8):
+        assert tiling.find_padding(v, 32) == ot.find_padding(v, 32)
