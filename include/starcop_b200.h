@@ -67,10 +67,11 @@ int sc_pack_weights(const float* w_oihw, float* w_packed, int Cout, int Cin, int
 /* depthwise 3x3, pad 1, stride 1|2; weights (C,1,3,3) f32 torch layout.
  * The *_bnact variants read x through the producer's BatchNorm+activation on the fly:
  * xin = act(x*scale[c]+shift[c]) (scale==NULL -> identity), so the x6 expanded tensor of an
- * inverted-residual block is never written normalised. */
+ * inverted-residual block is never written normalised.  stats != NULL: fprop also emits the
+ * BatchNorm partial-sum rows of its stored outputs (see sc_bn_stats; *stats_rows_host = row count). */
 int sc_dwconv_fprop(const void* x, int ldx, const float* scale, const float* shift, int act,
-                    const float* w, void* y, int ldy, int N, int H, int W, int C, int stride,
-                    int dtype, void* stream);
+                    const float* w, void* y, int ldy, double* stats, int* stats_rows_host, int N, int H, int W,
+                    int C, int stride, int dtype, void* stream);
 int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* dx, int lddx,
                     int N, int H, int W, int C, int stride, int dtype, void* stream);
 /* dw (C,1,3,3) += ...; workspace: sc_dwconv_wgrad_workspace_bytes(C) bytes of per-block partial rows */

@@ -22,7 +22,7 @@ SIGNATURES = {
     "sc_conv_fprop": [P, I, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P],
     "sc_conv_wgrad": [P, I, P, I, P, I, I, I, I, I, I, I, I, I, I, P],
     "sc_pack_weights": [P, P, I, I, I, I, I, P],
-    "sc_dwconv_fprop": [P, I, P, P, I, P, P, I, I, I, I, I, I, I, P],
+    "sc_dwconv_fprop": [P, I, P, P, I, P, P, I, P, P, I, I, I, I, I, I, P],
     "sc_dwconv_dgrad": [P, I, P, P, I, I, I, I, I, I, I, P],
     "sc_dwconv_wgrad_workspace_bytes": [I],
     "sc_dwconv_wgrad": [P, I, P, P, I, P, I, P, P, I, I, I, I, I, I, P],

@@ -1,7 +1,6 @@
 // fp32-FMA implicit-GEMM convolutions (NHWC).  This is the exact-fp32 path: it carries the parity
 // claim against the reference's fp32 PyTorch network and serves every layer the tcgen05 path does
-// not (stem Cin=4 stride 2, channel counts that are not multiples of 16).  Depthwise 3x3 kernels
-// (bandwidth bound) live here too.
+// not (stem Cin=4 stride 2, channel counts that are not multiples of 16).  The depthwise 3x3 kernels live in dwconv.cu.
 #include "common.cuh"
 
 using namespace sc;
@@ -300,347 +299,5 @@ extern "C" int sc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, f
   SC_DISPATCH_DTYPE(dtype, (conv_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
                                (const T*)x, ldx, (const T*)dy, lddy, dw_oihw, N, H, W, Cin, Cout, KH, KW, stride,
                                pad, Ho, Wo, ci_tiles, psplit)));
-  return check_launch();
-}
-
-// ------------------------------------------------------------------------------------------------
-// depthwise 3x3 (pad 1, stride 1|2), optional BN+act of the producer applied on load.
-// Bandwidth-bound: 8-channel vectors, weights staged once per block in shared memory as [tap][C]
-// (the torch layout [C][9] would cost 72 strided scalar loads per output vector).
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ f8 load_bnact(const T* p, const f8& sc_, const f8& sh, bool has_bn, int act) {
-  f8 v = load8<T>(p);
-  if (has_bn) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v.v[i] = apply_act(fmaf(v.v[i], sc_.v[i], sh.v[i]), act);
-  }
-  return v;
-}
-
-__device__ __forceinline__ void stage_dw_weights(float* ws, const float* __restrict__ w, int C) {
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
-    int c = i / 9, tap = i - c * 9;
-    ws[tap * C + c] = w[i];
-  }
-  __syncthreads();
-}
-
-// Each thread produces a strip of 4 horizontally adjacent outputs of one 8-channel vector: the
-// 3 x (3*stride+3) input window is loaded (and normalised) once instead of 9 loads per output.
-template <typename T, int STRIDE, int TW>
-__global__ void __launch_bounds__(256, (TW == 2 ? 3 : 1))
-dwconv_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int act, const float* __restrict__ w,
-                    T* __restrict__ y, int ldy, int N, int H, int W, int C, int Ho, int Wo) {
-  extern __shared__ float ws[];   // [9][C]
-  stage_dw_weights(ws, w, C);
-  constexpr int NI = (TW - 1) * STRIDE + 3;
-  const int CV = C / 8, WS = (Wo + TW - 1) / TW;
-  const int64_t total = (int64_t)N * Ho * WS * CV;
-  const bool has_bn = scale != nullptr;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % CV);
-    int64_t t = idx / CV;
-    const int wo0 = (int)(t % WS) * TW;
-    t /= WS;
-    const int ho = (int)(t % Ho);
-    const int n = (int)(t / Ho);
-    f8 sc_, sh;
-    if (has_bn) {
-      sc_ = load8<float>(scale + cv * 8);
-      sh = load8<float>(shift + cv * 8);
-    }
-    float acc[TW][8];
-#pragma unroll
-    for (int j = 0; j < TW; ++j)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
-    const int iw0 = wo0 * STRIDE - 1;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int ih = ho * STRIDE - 1 + kh;
-      if (ih < 0 || ih >= H) continue;
-      const T* xr = x + (((int64_t)n * H + ih) * W) * ldx + cv * 8;
-      f8 in[NI];
-#pragma unroll
-      for (int c = 0; c < NI; ++c) {
-        const int iw = iw0 + c;
-        if (iw >= 0 && iw < W) {
-          in[c] = load_bnact<T>(xr + (int64_t)iw * ldx, sc_, sh, has_bn, act);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) in[c].v[i] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const f8 wv = load8<float>(ws + (kh * 3 + kw) * C + cv * 8);
-#pragma unroll
-        for (int j = 0; j < TW; ++j)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(in[j * STRIDE + kw].v[i], wv.v[i], acc[j][i]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < TW; ++j) {
-      if (wo0 + j >= Wo) break;
-      f8 o;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = acc[j][i];
-      store8<T>(y + ((((int64_t)n * Ho + ho) * Wo) + wo0 + j) * ldy + cv * 8, o);
-    }
-  }
-}
-
-static int ew_blocks2(int64_t total) {
-  int64_t b = (total + 255) / 256;
-  int64_t cap = (int64_t)kNumSMs * 8;
-  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
-}
-
-extern "C" int sc_dwconv_fprop(const void* x, int ldx, const float* scale, const float* shift, int act,
-                               const float* w, void* y, int ldy, int N, int H, int W, int C, int stride, int dtype,
-                               void* stream) {
-  if (!x || !w || !y || C % 8 || ldx % 8 || ldy % 8 || (stride != 1 && stride != 2) || C > 1280) return SC_ERR_BAD_ARG;
-  int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  // measured on B200 (profiles/): stride 1 is fastest with 4-wide strips, stride 2 with 2-wide strips
-  // at 3 blocks per SM (these kernels are latency bound: occupancy vs. reuse)
-  const int tw = stride == 1 ? 4 : 2;
-  int64_t total = (int64_t)N * Ho * ((Wo + tw - 1) / tw) * (C / 8);
-  size_t smem = (size_t)9 * C * sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (stride == 1)
-    SC_DISPATCH_DTYPE(dtype, (dwconv_fprop_kernel<T, 1, 4><<<ew_blocks2(total), 256, smem, st>>>(
-                                 (const T*)x, ldx, scale, shift, act, w, (T*)y, ldy, N, H, W, C, Ho, Wo)));
-  else
-    SC_DISPATCH_DTYPE(dtype, (dwconv_fprop_kernel<T, 2, 2><<<ew_blocks2(total), 256, smem, st>>>(
-                                 (const T*)x, ldx, scale, shift, act, w, (T*)y, ldy, N, H, W, C, Ho, Wo)));
-  return check_launch();
-}
-
-// dx[n,ih,iw,c] = sum_{kh,kw : (ih+1-kh) % s == 0 ...} dy[n,(ih+1-kh)/s,(iw+1-kw)/s,c] * w[c,kh,kw]
-template <typename T>
-__global__ void __launch_bounds__(256)
-dwconv_dgrad_kernel(const T* __restrict__ dy, int lddy, const float* __restrict__ w,
-                    T* __restrict__ dx, int lddx, int N, int H, int W, int C, int stride, int Ho, int Wo) {
-  extern __shared__ float ws[];
-  stage_dw_weights(ws, w, C);
-  int CV = C / 8;
-  int64_t total = (int64_t)N * H * W * CV;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(idx % CV);
-    int64_t p = idx / CV;
-    int iw = (int)(p % W);
-    int64_t t = p / W;
-    int ih = (int)(t % H);
-    int n = (int)(t / H);
-    float acc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      int th = ih + 1 - kh;
-      if (th < 0 || th % stride) continue;
-      int ho = th / stride;
-      if (ho >= Ho) continue;
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        int tw = iw + 1 - kw;
-        if (tw < 0 || tw % stride) continue;
-        int wo = tw / stride;
-        if (wo >= Wo) continue;
-        f8 g = load8<T>(dy + (((int64_t)n * Ho + ho) * Wo + wo) * lddy + cv * 8);
-        f8 wv = load8<float>(ws + (kh * 3 + kw) * C + cv * 8);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(g.v[i], wv.v[i], acc[i]);
-      }
-    }
-    f8 o;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o.v[i] = acc[i];
-    store8<T>(dx + p * lddx + cv * 8, o);
-  }
-}
-
-// stride-1 data gradient = depthwise correlation of dy with the mirrored filter: same 4-wide strips
-template <typename T>
-__global__ void __launch_bounds__(256)
-dwconv_dgrad_s1_kernel(const T* __restrict__ dy, int lddy, const float* __restrict__ w, T* __restrict__ dx, int lddx,
-                       int N, int H, int W, int C) {
-  extern __shared__ float ws[];
-  stage_dw_weights(ws, w, C);
-  constexpr int TW = 4, NI = TW + 2;
-  const int CV = C / 8, WS = (W + TW - 1) / TW;
-  const int64_t total = (int64_t)N * H * WS * CV;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int cv = (int)(idx % CV);
-    int64_t t = idx / CV;
-    const int iw0 = (int)(t % WS) * TW;
-    t /= WS;
-    const int ih = (int)(t % H);
-    const int n = (int)(t / H);
-    float acc[TW][8];
-#pragma unroll
-    for (int j = 0; j < TW; ++j)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int oh = ih + 1 - kh;                 // dx[ih] += dy[ih+1-kh] * w[kh]
-      if (oh < 0 || oh >= H) continue;
-      const T* gr = dy + (((int64_t)n * H + oh) * W) * lddy + cv * 8;
-      f8 in[NI];
-#pragma unroll
-      for (int c = 0; c < NI; ++c) {
-        const int ow = iw0 - 1 + c;
-        if (ow >= 0 && ow < W) {
-          in[c] = load8<T>(gr + (int64_t)ow * lddy);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) in[c].v[i] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const f8 wv = load8<float>(ws + (kh * 3 + kw) * C + cv * 8);
-        // dx[iw0+j] += dy[iw0+j+1-kw] * w[kw]  ->  in[j + 2 - kw]
-#pragma unroll
-        for (int j = 0; j < TW; ++j)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(in[j + 2 - kw].v[i], wv.v[i], acc[j][i]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < TW; ++j) {
-      if (iw0 + j >= W) break;
-      f8 o;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) o.v[i] = acc[j][i];
-      store8<T>(dx + ((((int64_t)n * H + ih) * W) + iw0 + j) * lddx + cv * 8, o);
-    }
-  }
-}
-
-extern "C" int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* dx, int lddx, int N, int H, int W,
-                               int C, int stride, int dtype, void* stream) {
-  if (!dy || !w || !dx || C % 8 || lddy % 8 || lddx % 8 || (stride != 1 && stride != 2) || C > 1280) return SC_ERR_BAD_ARG;
-  int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  int64_t total = (int64_t)N * H * W * (C / 8);
-  size_t smem = (size_t)9 * C * sizeof(float);
-  if (stride == 1) {
-    int64_t strips = (int64_t)N * H * ((W + 3) / 4) * (C / 8);
-    SC_DISPATCH_DTYPE(dtype, (dwconv_dgrad_s1_kernel<T><<<ew_blocks2(strips), 256, smem, (cudaStream_t)stream>>>(
-                                 (const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C)));
-    return check_launch();
-  }
-  SC_DISPATCH_DTYPE(dtype, (dwconv_dgrad_kernel<T><<<ew_blocks2(total), 256, smem, (cudaStream_t)stream>>>(
-                               (const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C, stride, Ho, Wo)));
-  return check_launch();
-}
-
-// wgrad: thread = (pixel lane, 8-channel vector), 72 fp32 partials per thread; each block writes ONE
-// row of partial sums [C][9] to the workspace, a second tiny kernel adds the rows into dw.
-template <typename T>
-__global__ void __launch_bounds__(256)
-dwconv_wgrad_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
-                    const float* __restrict__ shift, int act, const T* __restrict__ dy, int lddy,
-                    float* __restrict__ partial, int N, int H, int W, int C, int stride, int Ho, int Wo,
-                    int CVB, int PL) {
-  extern __shared__ float smf[];   // [CVB*8][9]
-  int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
-  int cv = blockIdx.y * CVB + cvl;
-  for (int i = threadIdx.x; i < CVB * 72; i += blockDim.x) smf[i] = 0.f;
-  __syncthreads();
-  if (pl < PL && cv * 8 < C) {
-    f8 sc_, sh;
-    bool has_bn = scale != nullptr;
-    if (has_bn) {
-      sc_ = load8<float>(scale + cv * 8);
-      sh = load8<float>(shift + cv * 8);
-    }
-    float acc[9][8];
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[tp][i] = 0.f;
-    int64_t P = (int64_t)N * Ho * Wo;
-    for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
-      int wo = (int)(p % Wo);
-      int64_t t = p / Wo;
-      int ho = (int)(t % Ho);
-      int n = (int)(t / Ho);
-      f8 g = load8<T>(dy + p * lddy + cv * 8);
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        int ih = ho * stride - 1 + kh;
-        if (ih < 0 || ih >= H) continue;
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          int iw = wo * stride - 1 + kw;
-          if (iw < 0 || iw >= W) continue;
-          f8 v = load_bnact<T>(x + (((int64_t)n * H + ih) * W + iw) * ldx + cv * 8, sc_, sh, has_bn, act);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[kh * 3 + kw][i] = fmaf(v.v[i], g.v[i], acc[kh * 3 + kw][i]);
-        }
-      }
-    }
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&smf[(cvl * 8 + i) * 9 + tp], acc[tp][i]);
-  }
-  __syncthreads();
-  float* row = partial + (int64_t)blockIdx.x * C * 9;
-  for (int i = threadIdx.x; i < CVB * 72; i += blockDim.x) {
-    int c = blockIdx.y * CVB * 8 + i / 9;
-    if (c < C) row[c * 9 + i % 9] = smf[i];
-  }
-}
-
-__global__ void dwconv_wgrad_sum_kernel(const float* __restrict__ partial, int nrows, int n, float* __restrict__ dw) {
-  __shared__ float sh[8][33];
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int i = blockIdx.x * 32 + tx;
-  float s = 0.f;
-  if (i < n)
-    for (int r = ty; r < nrows; r += 8) s += partial[(int64_t)r * n + i];
-  sh[ty][tx] = s;
-  __syncthreads();
-  if (ty != 0 || i >= n) return;
-#pragma unroll
-  for (int j = 1; j < 8; ++j) s += sh[j][tx];
-  dw[i] += s;
-}
-
-constexpr int kDwMaxRows = 296;
-extern "C" int64_t sc_dwconv_wgrad_workspace_bytes(int C) { return (int64_t)kDwMaxRows * C * 9 * sizeof(float); }
-
-extern "C" int sc_dwconv_wgrad(const void* x, int ldx, const float* scale, const float* shift, int act,
-                               const void* dy, int lddy, float* dw, float* workspace, int N, int H, int W, int C,
-                               int stride, int dtype, void* stream) {
-  if (!x || !dy || !dw || !workspace || C % 8 || ldx % 8 || lddy % 8 || (stride != 1 && stride != 2))
-    return SC_ERR_BAD_ARG;
-  int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
-  int CV = C / 8;
-  int CVB = CV < 64 ? CV : 64;      // 64*72 floats = 18 KB smem
-  int PL = 256 / CVB;
-  int gy = (CV + CVB - 1) / CVB;
-  int64_t P = (int64_t)N * Ho * Wo;
-  int64_t want = (P + PL * 8 - 1) / (PL * 8);
-  int64_t cap = (kNumSMs * 4) / gy;
-  if (cap < 1) cap = 1;
-  if (cap > kDwMaxRows) cap = kDwMaxRows;
-  int bx = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-  dim3 grid(bx, gy);
-  size_t smem = (size_t)CVB * 72 * sizeof(float);
-  cudaStream_t st = (cudaStream_t)stream;
-  SC_DISPATCH_DTYPE(dtype, (dwconv_wgrad_kernel<T><<<grid, 256, smem, st>>>(
-                               (const T*)x, ldx, scale, shift, act, (const T*)dy, lddy, workspace, N, H, W, C, stride, Ho,
-                               Wo, CVB, PL)));
-  dwconv_wgrad_sum_kernel<<<(C * 9 + 31) / 32, dim3(32, 8), 0, st>>>(workspace, bx, C * 9, dw);
   return check_launch();
 }

@@ -155,18 +155,21 @@ extern "C" int sc_bn_stats(const void* y, int ldy, double* partials, int* nrows_
   return check_launch();
 }
 
-// block = 32 channels x 8 row slices: the nrows partial rows are summed 8-way in parallel
+// block = 32 channels x kRedY row slices: the nrows partial rows are summed kRedY-way in parallel
+// (<= 10 independent loads per thread: these tiny kernels are pure latency)
+constexpr int kRedY = 32;
 __global__ void bn_finalize_kernel(const double* __restrict__ partials, int nrows, int64_t P, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, float momentum, float eps,
                                    int training, float* scale, float* shift, float* save_mean,
                                    float* save_invstd) {
-  __shared__ double sh[2][8][33];
+  __shared__ double sh[2][kRedY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
   double s1 = 0.0, s2 = 0.0;
   if (training && c < C) {
-    for (int r = ty; r < nrows; r += 8) {
+#pragma unroll 4
+    for (int r = ty; r < nrows; r += kRedY) {
       s1 += partials[(int64_t)r * 2 * C + c];
       s2 += partials[(int64_t)r * 2 * C + C + c];
     }
@@ -177,8 +180,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partials, int nrow
   if (ty != 0 || c >= C) return;
   float mean, invstd;
   if (training) {
+    // fixed summation order: deterministic
 #pragma unroll
-    for (int j = 1; j < 8; ++j) {
+    for (int j = 1; j < kRedY; ++j) {
       s1 += sh[0][j][tx];
       s2 += sh[1][j][tx];
     }
@@ -210,7 +214,7 @@ extern "C" int sc_bn_finalize(const double* sums, int nrows, int64_t P, int C, c
                               float* save_invstd, void* stream) {
   if (C <= 0 || !scale || !shift || (training && !sums) || (!training && (!running_mean || !running_var)))
     return SC_ERR_BAD_ARG;
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, (cudaStream_t)stream>>>(
       sums, nrows, P, C, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift,
       save_mean, save_invstd);
   return check_launch();
@@ -413,21 +417,23 @@ __global__ void bn_bwd_totals_kernel(double* __restrict__ partials, int nrows, i
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      float* dgamma, float* dbeta, float* __restrict__ coef) {
-  __shared__ double sh[2][8][33];
+  __shared__ double sh[2][kRedY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
   double s1 = 0.0, s2 = 0.0;
-  if (c < C)
-    for (int r = ty; r < nrows; r += 8) {
+  if (c < C) {
+#pragma unroll 4
+    for (int r = ty; r < nrows; r += kRedY) {
       s1 += partials[(int64_t)r * 2 * C + c];
       s2 += partials[(int64_t)r * 2 * C + C + c];
     }
+  }
   sh[0][ty][tx] = s1;
   sh[1][ty][tx] = s2;
   __syncthreads();
   if (ty != 0 || c >= C) return;
 #pragma unroll
-  for (int j = 1; j < 8; ++j) {
+  for (int j = 1; j < kRedY; ++j) {
     s1 += sh[0][j][tx];
     s2 += sh[1][j][tx];
   }
@@ -457,7 +463,7 @@ extern "C" int sc_bn_bwd_apply(const void* dz, int lddz, int pooled, const void*
   int64_t P = (int64_t)N * H * W;
   // the coefficient table lives right after the totals row of the partials buffer (4*C floats = 2*C doubles)
   float* coef = reinterpret_cast<float*>(partials + ((int64_t)nrows + 1) * 2 * C);
-  bn_bwd_totals_kernel<<<(C + 31) / 32, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+  bn_bwd_totals_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, (cudaStream_t)stream>>>(
       partials, nrows, C, 1.0 / (double)P, scale, shift, mean, invstd, dgamma, dbeta, coef);
   RedGeom g = red_geom(C);
   int64_t want = (P + g.PL * 4 - 1) / (g.PL * 4);

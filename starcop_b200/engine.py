@@ -276,9 +276,11 @@ class UNetEngine:
         wdw, bn2 = f"{prefix}.conv.{i}.0.weight", f"{prefix}.conv.{i}.1"
         Ho, Wo = (x.H - 1) // stride + 1, (x.W - 1) // stride + 1
         y2 = self.new(x.N, Ho, Wo, hidden)
+        # the depthwise kernel emits the BatchNorm partial sums of its outputs: no statistics pass over y2
+        part2, n2 = (self._partials(hidden), ctypes.c_int(0)) if training else (0, ctypes.c_int(0))
         call("sc_dwconv_fprop", dw_in.ptr, dw_in.ld, dw_scale, dw_shift, dw_act, self.p[wdw].data_ptr(),
-             y2.ptr, y2.ld, x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
-        st2 = self._bn_forward(y2, bn2, training)
+             y2.ptr, y2.ld, part2, ctypes.byref(n2), x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
+        st2 = self._bn_forward(y2, bn2, training, (part2, n2.value) if training else None)
         z2 = self._bn_act(y2, st2[0], st2[1], ACT_RELU6)
         wpr, bn3 = f"{prefix}.conv.{i + 1}.weight", f"{prefix}.conv.{i + 2}"
         y3, sums3 = self._dense_fprop(z2, wpr, 1, 1, want_stats=training)

@@ -1,4 +1,6 @@
 """Per-kernel parity: each C-ABI entry point against plain PyTorch fp32 on the same seeded inputs."""
+import ctypes
+
 import numpy as np
 import pytest
 import torch
@@ -75,7 +77,8 @@ def test_conv_fprop_wgrad_dgrad(dtype, cin, cout, k, stride, hw):
 
 
 @pytest.mark.parametrize("dtype", [SC_F32, SC_BF16])
-@pytest.mark.parametrize("c,stride,hw,fused", [(32, 1, 16, False), (96, 2, 16, True), (144, 1, 8, True), (960, 1, 4, True)])
+@pytest.mark.parametrize("c,stride,hw,fused", [(32, 1, 16, False), (96, 2, 16, True), (144, 1, 8, True), (960, 1, 4, True),
+                                               (48, 1, 37, True), (24, 2, 31, False), (64, 2, 64, True), (192, 1, 40, True)])
 def test_depthwise(dtype, c, stride, hw, fused):
     torch.manual_seed(1)
     N = 2
@@ -90,8 +93,19 @@ def test_depthwise(dtype, c, stride, hw, fused):
     ho = yr.shape[-1]
     y = torch.empty(N, ho, ho, c, device=DEV, dtype=TDT[dtype])
     sp, hp, act = (scale.data_ptr(), shift.data_ptr(), ACT_RELU6) if fused else (0, 0, ACT_NONE)
-    call("sc_dwconv_fprop", xh.data_ptr(), c, sp, hp, act, w.data_ptr(), y.data_ptr(), c, N, hw, hw, c, stride, dtype, st())
+    part = torch.full((load().sc_bn_partials_bytes(c) // 8,), float("nan"), dtype=torch.float64, device=DEV)
+    nrows = ctypes.c_int(0)
+    call("sc_dwconv_fprop", xh.data_ptr(), c, sp, hp, act, w.data_ptr(), y.data_ptr(), c, part.data_ptr(),
+         ctypes.byref(nrows), N, hw, hw, c, stride, dtype, st())
     assert torch.allclose(nchw(y), yr, **tol(dtype))
+    # fused BatchNorm partial rows = sum / sum of squares of the STORED outputs
+    rows = part[:nrows.value * 2 * c].view(nrows.value, 2 * c).sum(0)
+    yf = y.float().reshape(-1, c).double()
+    assert torch.allclose(rows[:c], yf.sum(0), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(rows[c:], (yf * yf).sum(0), rtol=1e-5, atol=1e-4)
+    y2 = torch.empty_like(y)
+    call("sc_dwconv_fprop", xh.data_ptr(), c, sp, hp, act, w.data_ptr(), y2.data_ptr(), c, 0, 0, N, hw, hw, c, stride, dtype, st())
+    assert torch.equal(y, y2)
     dy = nhwc(torch.randn_like(yr), dtype)
     gin = torch.autograd.grad(yr, [xin, wr], dy.float().permute(0, 3, 1, 2))
     dx = torch.empty(N, hw, hw, c, device=DEV, dtype=TDT[dtype])
