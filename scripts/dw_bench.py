@@ -14,6 +14,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=16)
 ap.add_argument("--size", type=int, default=512)
 ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--only", default="")
 a = ap.parse_args()
 lib = _lib.load()
 B, S = a.batch, a.size
@@ -37,6 +38,8 @@ def timeit(fn):
 tot = {"fprop": 0.0, "dgrad": 0.0, "wgrad": 0.0}
 print(f"{'layer':8s} {'op':6s} {'us':>8s} {'GB/s':>8s}  shape")
 for name, C, div, s in layers:
+    if a.only and name not in a.only.split(","):
+        continue
     H = S // div
     Ho = H // s
     xs = [torch.randn(B, H, H, C, device="cuda").bfloat16() for _ in range(NB)]      # rotating buffers: cold L2

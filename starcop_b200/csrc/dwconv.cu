@@ -2,11 +2,12 @@
 //
 // These are HBM-bound stencils (9 MACs per element moved).  Every kernel here is a persistent CTA
 // that walks spatial tiles of one channel block: the input halo tile is staged ONCE into shared
-// memory with the producer's BatchNorm + activation already applied (so the x6 expanded tensor of
-// an inverted-residual block is never stored normalised, and each element is normalised once, not
-// once per tap), then outputs are computed from shared memory in register strips.  All global loads
-// happen in the staging loops (many independent 16 B loads in flight per thread); several CTAs per
-// SM overlap one CTA's staging with another's arithmetic.
+// memory by TMA (one 4-D box per tile, zero fill outside the image, a ring of 2-3 tiles in flight per CTA
+// so the HBM pipe stays full while the CTA computes), normalised IN PLACE with the producer's
+// BatchNorm + activation (so the x6 expanded tensor of an inverted-residual block is never stored
+// normalised, and each element is normalised once, not once per tap), then outputs are computed from
+// shared memory in register strips.  Tile geometry and the channel-block width are compile-time
+// constants, so every shared-memory address is base + immediate.
 //   * fprop optionally emits the BatchNorm partial-sum rows of its (stored) outputs, which removes
 //     the separate statistics pass over y;
 //   * stride-1 dgrad is fprop with the mirrored filter; stride-2 dgrad computes 2x2 output quads
@@ -14,201 +15,236 @@
 //   * wgrad keeps the 9 x 8 tap sums of a thread's channel vector in registers across all its
 //     tiles and writes ONE partial row per CTA (deterministic two-level reduction, no atomics).
 #include "common.cuh"
+#include "tc_common.cuh"
 
 using namespace sc;
+using namespace tc;
 
 namespace {
 
 constexpr int kDwThreads = 256;
+#ifndef DW_FPROP_MINB
+#define DW_FPROP_MINB 3
+#endif
+#ifndef DW_FPROP_CTAS
+#define DW_FPROP_CTAS 3
+#endif
 constexpr int kDwMaxRows = 296;
 
-struct DwPlan {
-  int TH, TW;            // output tile (for the stride-2 dgrad: tile in dy space)
-  int IH, IW;            // staged input tile
-  int CVB, n_cb;         // 8-channel vectors per block, channel blocks
-  int tiles_h, tiles_w;
-  int64_t n_tiles;       // N * tiles_h * tiles_w
-  int grid_x;
+// compile-time tile geometry for stride S, CVB 8-channel vectors per block, strips of TWP outputs
+template <int S, int CVB, int TWP>
+struct DwGeo {
+  static constexpr int PLn = kDwThreads / CVB;                       // pixel lanes (threads per channel vector)
+  static constexpr int TW = 16;
+  static constexpr int STRIPS = TW / TWP;
+  static constexpr int TH0 = S == 1 ? 8 : 4;
+  static constexpr int TH = (TH0 * STRIPS >= PLn) ? TH0 : 2 * TH0;   // every lane gets >= 1 strip per tile
+  static constexpr int IH = (TH - 1) * S + 3, IW = (TW - 1) * S + 3;
+  static constexpr int ITEMS = TH * STRIPS;
+  static constexpr int TILE_ELEMS = IH * IW * CVB * 8;
 };
 
-static int pick_cvb(int CV) {
-  for (int d = 8; d >= 1; --d)
-    if (CV % d == 0) return d;
-  return 1;
-}
+struct DwTiles {
+  int tiles_h, tiles_w;
+  int n_tiles;           // N * tiles_h * tiles_w
+};
 
-static DwPlan dw_plan(int N, int Ho, int Wo, int CV, int th, int tw, int ih, int iw, int ctas_per_sm, int max_rows) {
-  DwPlan p;
-  p.TH = th;
-  p.TW = tw;
-  p.IH = ih;
-  p.IW = iw;
-  p.CVB = pick_cvb(CV);
-  p.n_cb = CV / p.CVB;
-  p.tiles_h = (Ho + th - 1) / th;
-  p.tiles_w = (Wo + tw - 1) / tw;
-  p.n_tiles = (int64_t)N * p.tiles_h * p.tiles_w;
-  int64_t cap = ((int64_t)kNumSMs * ctas_per_sm + p.n_cb - 1) / p.n_cb;
-  if (cap < 1) cap = 1;
-  if (cap > max_rows) cap = max_rows;
-  p.grid_x = (int)(p.n_tiles < cap ? p.n_tiles : cap);
-  return p;
-}
-
-// Stage act(x*scale+shift) of the halo tile [ih0, ih0+IH) x [iw0, iw0+IW) of image n, channel vectors
-// [cv0, cv0+CVB), into sm[(px*CVB + cvl)*8]; out-of-image elements are ZERO (the conv's padding applies
-// to the normalised tensor).
-template <typename T>
-__device__ __forceinline__ void dw_stage(T* __restrict__ sm, const T* __restrict__ x, int ldx, int n, int ih0, int iw0,
-                                         int IH, int IW, int H, int W, int cv0, int CVB, const float* s_bn, int act,
-                                         int cvl, int pl, int PLn) {
-  // s_bn: shared [2][CVB*8] scale | shift of this channel block, or nullptr (identity).  Loaded here so the
-  // 16 registers are not live during the arithmetic phase.
-  const bool has_bn = s_bn != nullptr;
-  f8 sc_, sh;
-  if (has_bn) {
-    sc_ = load8<float>(s_bn + cvl * 8);
-    sh = load8<float>(s_bn + CVB * 8 + cvl * 8);
-  }
-  const int npx = IH * IW;
-  const T* xn = x + (int64_t)n * H * W * ldx + (cv0 + cvl) * 8;
-#pragma unroll 4
-  for (int px = pl; px < npx; px += PLn) {
+// The staged tile holds RAW values (TMA zero-filled outside the image).  Normalise it in place:
+// v <- act(v*scale+shift) inside the image, 0 outside (the conv's padding applies to the NORMALISED
+// tensor, and act(shift) != 0).  s_bn: shared [2][CVB*8] scale | shift.
+template <typename T, int IH, int IW, int CVB>
+__device__ __forceinline__ void dw_normalize(T* __restrict__ sm, int ih0, int iw0, int H, int W, const float* s_bn,
+                                             int act, int cvl, int pl) {
+  constexpr int PLn = kDwThreads / CVB;
+  const f8 sc_ = load8<float>(s_bn + cvl * 8), sh = load8<float>(s_bn + CVB * 8 + cvl * 8);
+#pragma unroll 2
+  for (int px = pl; px < IH * IW; px += PLn) {
     const int r = px / IW, c = px - r * IW;
     const int ih = ih0 + r, iw = iw0 + c;
+    T* p = sm + (px * CVB + cvl) * 8;
     f8 v;
-    if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
-      v = load8<T>(xn + ((int64_t)ih * W + iw) * ldx);
-      if (has_bn) {
+    if ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) {
+      v = load8<T>(p);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v.v[i] = apply_act(fmaf(v.v[i], sc_.v[i], sh.v[i]), act);
-      }
+      for (int i = 0; i < 8; ++i) v.v[i] = apply_act(fmaf(v.v[i], sc_.v[i], sh.v[i]), act);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v.v[i] = 0.f;
     }
-    store8<T>(sm + ((size_t)px * CVB + cvl) * 8, v);
+    store8<T>(p, v);
   }
 }
 
+// ring of `ns` staged tiles, one mbarrier each; the CTA's i-th tile lives in slot i % ns
+struct DwRing {
+  uint8_t* bufs;
+  uint64_t* full;
+  int ns, stage_bytes;
+};
+__device__ __forceinline__ DwRing dw_ring_init(uint8_t* smem_aligned, int ns, int stage_bytes) {
+  DwRing r;
+  r.bufs = smem_aligned;
+  r.full = reinterpret_cast<uint64_t*>(smem_aligned + (size_t)ns * stage_bytes);
+  r.ns = ns;
+  r.stage_bytes = stage_bytes;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ns; ++i) mbar_init(&r.full[i], 1);
+    fence_barrier_init();
+  }
+  return r;
+}
 __device__ __forceinline__ const float* dw_stage_bn(float* s_bn, const float* __restrict__ scale,
-                                                    const float* __restrict__ shift, int cv0, int CVB) {
+                                                    const float* __restrict__ shift, int cv0, int n) {
   if (!scale) return nullptr;
-  for (int i = threadIdx.x; i < CVB * 8; i += blockDim.x) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     s_bn[i] = scale[cv0 * 8 + i];
-    s_bn[CVB * 8 + i] = shift[cv0 * 8 + i];
+    s_bn[n + i] = shift[cv0 * 8 + i];
   }
   return s_bn;
 }
 
+__device__ __forceinline__ void dw_tile_coords(int t, const DwTiles& g, int& n, int& th, int& tw) {
+  tw = t % g.tiles_w;
+  const int t2 = t / g.tiles_w;
+  th = t2 % g.tiles_h;
+  n = t2 / g.tiles_h;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // fprop (and stride-1 dgrad with mirror = 1): thread = (strip of TWP outputs, channel vector)
+// shared memory: [ns x stage][ns mbarriers][9*CVB*8 weights | 2*CVB*8 scale, shift]
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int STRIDE, int TWP>
-__global__ void __launch_bounds__(kDwThreads, 3)
-dw_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale, const float* __restrict__ shift,
-                int act, const float* __restrict__ w, int mirror, T* __restrict__ y, int ldy,
-                double* __restrict__ stats, int H, int W, int C, int Ho, int Wo, DwPlan g) {
-  extern __shared__ __align__(16) uint8_t dw_smem[];
-  const int CVB = g.CVB;
-  float* ws = reinterpret_cast<float*>(dw_smem);                 // [9][CVB*8] weights, [2][CVB*8] scale | shift
-  T* tile = reinterpret_cast<T*>(ws + 11 * CVB * 8);             // [IH*IW][CVB][8]
+template <typename T, int S, int CVB>
+__global__ void __launch_bounds__(kDwThreads, DW_FPROP_MINB)
+dw_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ scale,
+                const float* __restrict__ shift, int act, const float* __restrict__ w, int mirror, T* __restrict__ y,
+                int ldy, double* __restrict__ stats, int H, int W, int C, int Ho, int Wo, DwTiles g, int ns,
+                int stage_bytes) {
+  constexpr int TWP = S == 1 ? 4 : 2;
+  using G = DwGeo<S, CVB, TWP>;
+  constexpr int NI = (TWP - 1) * S + 3;
+  constexpr uint32_t kTileBytes = G::TILE_ELEMS * sizeof(T);
+  extern __shared__ __align__(128) uint8_t dw_smem[];   // no integer casts: keeps the shared address space (LDS, not LD)
+  DwRing ring = dw_ring_init(dw_smem, ns, stage_bytes);
+  float* ws = reinterpret_cast<float*>(ring.full + ns + (ns & 1));   // 16 B aligned
   const int tid = threadIdx.x;
-  const int PLn = kDwThreads / CVB;
   const int cvl = tid % CVB, pl = tid / CVB;
-  const bool active = pl < PLn;
+  const bool active = pl < G::PLn;
   const int cv0 = blockIdx.y * CVB;
   for (int i = tid; i < 9 * CVB * 8; i += kDwThreads) {
     const int tap = i / (CVB * 8), c = i - tap * CVB * 8;
-    ws[i] = w[(int64_t)(cv0 * 8 + c) * 9 + (mirror ? 8 - tap : tap)];
+    ws[i] = w[(cv0 * 8 + c) * 9 + (mirror ? 8 - tap : tap)];
   }
-  const float* s_bn = dw_stage_bn(ws + 9 * CVB * 8, scale, shift, cv0, CVB);
+  const float* s_bn = dw_stage_bn(ws + 9 * CVB * 8, scale, shift, cv0, CVB * 8);
   float ssum[8], ssq[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) ssum[i] = ssq[i] = 0.f;
-  constexpr int NI = (TWP - 1) * STRIDE + 3;
-  const int strips_w = g.TW / TWP;
-  const int items = g.TH * strips_w;
-  for (int64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
-    const int tw = (int)(t % g.tiles_w);
-    const int64_t t2 = t / g.tiles_w;
-    const int th = (int)(t2 % g.tiles_h);
-    const int n = (int)(t2 / g.tiles_h);
-    const int oh0 = th * g.TH, ow0 = tw * g.TW;
-    __syncthreads();                               // the previous tile's readers are done (and ws is staged)
-    if (active)
-      dw_stage<T>(tile, x, ldx, n, oh0 * STRIDE - 1, ow0 * STRIDE - 1, g.IH, g.IW, H, W, cv0, CVB, s_bn, act, cvl, pl,
-                  PLn);
-    __syncthreads();
-    if (!active) continue;
-    for (int it = pl; it < items; it += PLn) {
-      const int r = it / strips_w, sw = it - r * strips_w;
-      const int oh = oh0 + r, ow = ow0 + sw * TWP;
-      if (oh >= Ho || ow >= Wo) continue;
-      float acc[TWP][8];
+  const float* wsc = ws + cvl * 8;
+  const int my_tiles = (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto issue = [&](int i) {     // thread 0: TMA the CTA's i-th tile into slot i % ns
+    int n, th, tw;
+    dw_tile_coords(blockIdx.x + i * gridDim.x, g, n, th, tw);
+    const int slot = i % ns;
+    mbar_arrive_expect_tx(&ring.full[slot], kTileBytes);
+    tma_load_4d(ring.bufs + (size_t)slot * stage_bytes, &tmX, cv0 * 8, tw * G::TW * S - 1, th * G::TH * S - 1, n,
+                &ring.full[slot]);
+  };
+  __syncthreads();                                 // barriers initialised, weights staged
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < ns && i < my_tiles; ++i) issue(i);
+  }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int i = 0; i < my_tiles; ++i) {
+    int n, th, tw;
+    dw_tile_coords(blockIdx.x + i * gridDim.x, g, n, th, tw);
+    const int oh0 = th * G::TH, ow0 = tw * G::TW;
+    T* tile = reinterpret_cast<T*>(ring.bufs + (size_t)slot * stage_bytes);
+    mbar_wait(&ring.full[slot], phase);
+    if (s_bn) {
+      if (active) dw_normalize<T, G::IH, G::IW, CVB>(tile, oh0 * S - 1, ow0 * S - 1, H, W, s_bn, act, cvl, pl);
+      __syncthreads();
+    }
+    if (active) {
+#pragma unroll 1
+      for (int it = pl; it < G::ITEMS; it += G::PLn) {
+        const int r = it / G::STRIPS, sw = it - r * G::STRIPS;
+        const int oh = oh0 + r, ow = ow0 + sw * TWP;
+        if (oh >= Ho || ow >= Wo) continue;
+        float acc[TWP][8];
 #pragma unroll
-      for (int j = 0; j < TWP; ++j)
+        for (int j = 0; j < TWP; ++j)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+          for (int k = 0; k < 8; ++k) acc[j][k] = 0.f;
+        const T* tp0 = tile + ((r * S * G::IW + sw * TWP * S) * CVB + cvl) * 8;
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const T* row = tile + ((size_t)((r * STRIDE + kh) * g.IW + sw * TWP * STRIDE) * CVB + cvl) * 8;
-        f8 wv[3];
+        for (int kh = 0; kh < 3; ++kh) {
+          f8 wv[3];
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) wv[kw] = load8<float>(ws + (kh * 3 + kw) * CVB * 8 + cvl * 8);
-        // one input vector live at a time: column c feeds output j through tap kw = c - j*STRIDE
+          for (int kw = 0; kw < 3; ++kw) wv[kw] = load8<float>(wsc + (kh * 3 + kw) * CVB * 8);
+          // one input vector live at a time: column c feeds output j through tap kw = c - j*S
 #pragma unroll
-        for (int c = 0; c < NI; ++c) {
-          const f8 in = load8<T>(row + (size_t)c * CVB * 8);
+          for (int c = 0; c < NI; ++c) {
+            const f8 in = load8<T>(tp0 + (kh * G::IW + c) * CVB * 8);
 #pragma unroll
-          for (int j = 0; j < TWP; ++j) {
-            const int kw = c - j * STRIDE;
-            if (kw >= 0 && kw < 3) {
+            for (int j = 0; j < TWP; ++j) {
+              const int kw = c - j * S;
+              if (kw >= 0 && kw < 3) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(in.v[i], wv[kw].v[i], acc[j][i]);
+                for (int k = 0; k < 8; ++k) acc[j][k] = fmaf(in.v[k], wv[kw].v[k], acc[j][k]);
+              }
+            }
+          }
+        }
+        T* yp = y + ((int64_t)(n * Ho + oh) * Wo + ow) * ldy + (cv0 + cvl) * 8;
+#pragma unroll
+        for (int j = 0; j < TWP; ++j) {
+          if (ow + j >= Wo) break;
+          f8 o;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o.v[k] = acc[j][k];
+          store8<T>(yp + (int64_t)j * ldy, o);
+          if (stats) {
+            // statistics of the STORED (storage-precision) values, like the separate pass would see them
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float sv = to_f<T>(from_f<T>(o.v[k]));
+              ssum[k] += sv;
+              ssq[k] = fmaf(sv, sv, ssq[k]);
             }
           }
         }
       }
-      T* yp = y + (((int64_t)n * Ho + oh) * Wo + ow) * ldy + (cv0 + cvl) * 8;
-#pragma unroll
-      for (int j = 0; j < TWP; ++j) {
-        if (ow + j >= Wo) break;
-        f8 o;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) o.v[i] = acc[j][i];
-        store8<T>(yp + (int64_t)j * ldy, o);
-        if (stats) {
-          // statistics of the STORED (storage-precision) values, like the separate pass would see them
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float s = to_f<T>(from_f<T>(o.v[i]));
-            ssum[i] += s;
-            ssq[i] = fmaf(s, s, ssq[i]);
-          }
-        }
-      }
+    }
+    __syncthreads();                               // every reader of this slot is done
+    if (tid == 0 && i + ns < my_tiles) {
+      fence_proxy_async();                         // generic-proxy accesses to the slot precede the async refill
+      issue(i + ns);
+    }
+    if (++slot == ns) {
+      slot = 0;
+      phase ^= 1;
     }
   }
   if (stats) {
     // deterministic block reduction: stage [pl][cvl][16] floats, then 16*CVB threads sum over pl in fixed order
-    __syncthreads();
-    float* red = reinterpret_cast<float*>(tile);               // >= 256*16*4 = 16 KB guaranteed by the launcher
+    float* red = reinterpret_cast<float*>(ring.bufs);          // >= 256*16*4 = 16 KB guaranteed by the launcher
     if (active) {
-      float* mine = red + ((size_t)pl * CVB + cvl) * 16;
+      float* mine = red + (pl * CVB + cvl) * 16;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        mine[i] = ssum[i];
-        mine[8 + i] = ssq[i];
+      for (int k = 0; k < 8; ++k) {
+        mine[k] = ssum[k];
+        mine[8 + k] = ssq[k];
       }
     }
     __syncthreads();
     double* row = stats + (int64_t)blockIdx.x * 2 * C;
     for (int o = tid; o < CVB * 16; o += kDwThreads) {
       const int cvo = o / 16, k = o % 16;
-      double s = 0.0;
-      for (int j = 0; j < PLn; ++j) s += (double)red[((size_t)j * CVB + cvo) * 16 + k];
-      row[(k < 8 ? 0 : C) + (cv0 + cvo) * 8 + (k & 7)] = s;
+      double sd = 0.0;
+      for (int j = 0; j < G::PLn; ++j) sd += (double)red[(j * CVB + cvo) * 16 + k];
+      row[(k < 8 ? 0 : C) + (cv0 + cvo) * 8 + (k & 7)] = sd;
     }
   }
 }
@@ -220,144 +256,214 @@ dw_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scal
 //   dx[2a+1,2b  ] = g10 w01 + g00 w21
 //   dx[2a+1,2b+1] = g11 w00 + g10 w02 + g01 w20 + g00 w22          (gXY = dy[a+X][b+Y], zero outside)
 // ---------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(kDwThreads)
-dw_dgrad_s2_kernel(const T* __restrict__ dy, int lddy, const float* __restrict__ w, T* __restrict__ dx, int lddx,
-                   int H, int W, int C, int Ho, int Wo, DwPlan g) {
-  extern __shared__ __align__(16) uint8_t dw_smem[];
-  const int CVB = g.CVB;
-  float* ws = reinterpret_cast<float*>(dw_smem);
-  T* tile = reinterpret_cast<T*>(ws + 9 * CVB * 8);
+template <int CVB>
+struct DwGeoD2 {
+  static constexpr int PLn = kDwThreads / CVB;
+  static constexpr int TW = 16;
+  static constexpr int TH = (8 * TW >= PLn * 2) ? 8 : 16;      // >= 2 quads per lane
+  static constexpr int IH = TH + 1, IW = TW + 1;
+  static constexpr int TILE_ELEMS = IH * IW * CVB * 8;
+};
+
+template <typename T, int CVB>
+__global__ void __launch_bounds__(kDwThreads, 3)
+dw_dgrad_s2_kernel(const __grid_constant__ CUtensorMap tmDY, const float* __restrict__ w, T* __restrict__ dx, int lddx,
+                   int H, int W, int C, DwTiles g, int ns, int stage_bytes) {
+  using G = DwGeoD2<CVB>;
+  constexpr int IW = G::IW;
+  constexpr uint32_t kTileBytes = G::TILE_ELEMS * sizeof(T);
+  extern __shared__ __align__(128) uint8_t dw_smem[];   // no integer casts: keeps the shared address space (LDS, not LD)
+  DwRing ring = dw_ring_init(dw_smem, ns, stage_bytes);
+  float* ws = reinterpret_cast<float*>(ring.full + ns + (ns & 1));
   const int tid = threadIdx.x;
-  const int PLn = kDwThreads / CVB;
   const int cvl = tid % CVB, pl = tid / CVB;
-  const bool active = pl < PLn;
+  const bool active = pl < G::PLn;
   const int cv0 = blockIdx.y * CVB;
   for (int i = tid; i < 9 * CVB * 8; i += kDwThreads) {
     const int tap = i / (CVB * 8), c = i - tap * CVB * 8;
-    ws[i] = w[(int64_t)(cv0 * 8 + c) * 9 + tap];
+    ws[i] = w[(cv0 * 8 + c) * 9 + tap];
   }
-  const int items = g.TH * g.TW;
-  for (int64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
-    const int tw = (int)(t % g.tiles_w);
-    const int64_t t2 = t / g.tiles_w;
-    const int th = (int)(t2 % g.tiles_h);
-    const int n = (int)(t2 / g.tiles_h);
-    const int a0 = th * g.TH, b0 = tw * g.TW;
-    __syncthreads();
-    if (active) dw_stage<T>(tile, dy, lddy, n, a0, b0, g.IH, g.IW, Ho, Wo, cv0, CVB, nullptr, 0, cvl, pl, PLn);
-    __syncthreads();
-    if (!active) continue;
-    for (int it = pl; it < items; it += PLn) {
-      const int r = it / g.TW, c = it - r * g.TW;
-      const int a = a0 + r, b = b0 + c;
-      if (2 * a >= H || 2 * b >= W) continue;
-      const T* tp = tile + ((size_t)(r * g.IW + c) * CVB + cvl) * 8;
-      const f8 g00 = load8<T>(tp), g01 = load8<T>(tp + (size_t)CVB * 8);
-      const f8 g10 = load8<T>(tp + (size_t)g.IW * CVB * 8), g11 = load8<T>(tp + (size_t)(g.IW + 1) * CVB * 8);
-      const float* wc = ws + cvl * 8;
-      const int WS = CVB * 8;
-      f8 o00, o01, o10, o11;
-      {
-        const f8 w11 = load8<float>(wc + 4 * WS), w10 = load8<float>(wc + 3 * WS), w12 = load8<float>(wc + 5 * WS);
+  const float* wc = ws + cvl * 8;
+  constexpr int WS = CVB * 8;
+  const int my_tiles = (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto issue = [&](int i) {
+    int n, th, tw;
+    dw_tile_coords(blockIdx.x + i * gridDim.x, g, n, th, tw);
+    const int slot = i % ns;
+    mbar_arrive_expect_tx(&ring.full[slot], kTileBytes);
+    tma_load_4d(ring.bufs + (size_t)slot * stage_bytes, &tmDY, cv0 * 8, tw * G::TW, th * G::TH, n, &ring.full[slot]);
+  };
+  __syncthreads();
+  if (tid == 0) {
+    tma_prefetch_desc(&tmDY);
+    for (int i = 0; i < ns && i < my_tiles; ++i) issue(i);
+  }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int i = 0; i < my_tiles; ++i) {
+    int n, th, tw;
+    dw_tile_coords(blockIdx.x + i * gridDim.x, g, n, th, tw);
+    const int a0 = th * G::TH, b0 = tw * G::TW;
+    const T* tile = reinterpret_cast<const T*>(ring.bufs + (size_t)slot * stage_bytes);
+    mbar_wait(&ring.full[slot], phase);
+    if (active) {
+#pragma unroll 1
+      for (int it = pl; it < G::TH * G::TW; it += G::PLn) {
+        const int r = it / G::TW, c = it - r * G::TW;
+        const int a = a0 + r, b = b0 + c;
+        if (2 * a >= H || 2 * b >= W) continue;
+        const T* tp = tile + ((r * IW + c) * CVB + cvl) * 8;
+        const f8 g00 = load8<T>(tp), g01 = load8<T>(tp + CVB * 8);
+        const f8 g10 = load8<T>(tp + IW * CVB * 8), g11 = load8<T>(tp + (IW + 1) * CVB * 8);
+        f8 o00, o01, o10, o11;
+        {
+          const f8 w11 = load8<float>(wc + 4 * WS), w10 = load8<float>(wc + 3 * WS), w12 = load8<float>(wc + 5 * WS);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          o00.v[i] = g00.v[i] * w11.v[i];
-          o01.v[i] = fmaf(g01.v[i], w10.v[i], g00.v[i] * w12.v[i]);
+          for (int k = 0; k < 8; ++k) {
+            o00.v[k] = g00.v[k] * w11.v[k];
+            o01.v[k] = fmaf(g01.v[k], w10.v[k], g00.v[k] * w12.v[k]);
+          }
         }
-      }
-      {
-        const f8 w01 = load8<float>(wc + 1 * WS), w21 = load8<float>(wc + 7 * WS);
+        {
+          const f8 w01 = load8<float>(wc + 1 * WS), w21 = load8<float>(wc + 7 * WS);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o10.v[i] = fmaf(g10.v[i], w01.v[i], g00.v[i] * w21.v[i]);
-      }
-      {
-        const f8 w00 = load8<float>(wc), w02 = load8<float>(wc + 2 * WS), w20 = load8<float>(wc + 6 * WS),
-                 w22 = load8<float>(wc + 8 * WS);
+          for (int k = 0; k < 8; ++k) o10.v[k] = fmaf(g10.v[k], w01.v[k], g00.v[k] * w21.v[k]);
+        }
+        {
+          const f8 w00 = load8<float>(wc), w02 = load8<float>(wc + 2 * WS), w20 = load8<float>(wc + 6 * WS),
+                   w22 = load8<float>(wc + 8 * WS);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          o11.v[i] = fmaf(g11.v[i], w00.v[i], fmaf(g10.v[i], w02.v[i], fmaf(g01.v[i], w20.v[i], g00.v[i] * w22.v[i])));
+          for (int k = 0; k < 8; ++k)
+            o11.v[k] = fmaf(g11.v[k], w00.v[k], fmaf(g10.v[k], w02.v[k], fmaf(g01.v[k], w20.v[k], g00.v[k] * w22.v[k])));
+        }
+        T* op = dx + ((int64_t)(n * H + 2 * a) * W + 2 * b) * lddx + (cv0 + cvl) * 8;
+        const bool w1 = 2 * b + 1 < W, h1 = 2 * a + 1 < H;
+        store8<T>(op, o00);
+        if (w1) store8<T>(op + lddx, o01);
+        if (h1) store8<T>(op + (int64_t)W * lddx, o10);
+        if (h1 && w1) store8<T>(op + ((int64_t)W + 1) * lddx, o11);
       }
-      T* op = dx + (((int64_t)n * H + 2 * a) * W + 2 * b) * lddx + (cv0 + cvl) * 8;
-      const bool w1 = 2 * b + 1 < W, h1 = 2 * a + 1 < H;
-      store8<T>(op, o00);
-      if (w1) store8<T>(op + lddx, o01);
-      if (h1) store8<T>(op + (int64_t)W * lddx, o10);
-      if (h1 && w1) store8<T>(op + ((int64_t)W + 1) * lddx, o11);
+    }
+    __syncthreads();
+    if (tid == 0 && i + ns < my_tiles) {
+      fence_proxy_async();
+      issue(i + ns);
+    }
+    if (++slot == ns) {
+      slot = 0;
+      phase ^= 1;
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// wgrad: dw[c][kh][kw] = sum_p xhat[p*s-1+k][c] * dy[p][c]; thread = (output pixel, channel vector)
+// wgrad: dw[c][kh][kw] = sum_p xhat[p*s-1+k][c] * dy[p][c]; thread = (strip of 2 outputs, channel vector)
+// one stage = [x halo tile][dy tile] (two TMA boxes on one mbarrier)
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int STRIDE>
+template <typename T, int S, int CVB>
 __global__ void __launch_bounds__(kDwThreads, 2)
-dw_wgrad_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale, const float* __restrict__ shift,
-                int act, const T* __restrict__ dy, int lddy, float* __restrict__ partial, int H, int W, int C, int Ho,
-                int Wo, DwPlan g) {
-  extern __shared__ __align__(16) uint8_t dw_smem[];
-  const int CVB = g.CVB;
-  float* s_bnbuf = reinterpret_cast<float*>(dw_smem);            // [2][CVB*8] scale | shift
-  T* tile = reinterpret_cast<T*>(s_bnbuf + 2 * CVB * 8);         // [IH*IW][CVB][8]
-  T* gt = tile + (size_t)g.IH * g.IW * CVB * 8;                  // [TH*TW][CVB][8] staged dy
+dw_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                const float* __restrict__ scale, const float* __restrict__ shift, int act, float* __restrict__ partial,
+                int H, int W, int C, DwTiles g, int ns, int stage_bytes) {
+  constexpr int TWP = 2;
+  using G = DwGeo<S, CVB, TWP>;
+  constexpr int NI = (TWP - 1) * S + 3;
+  constexpr uint32_t kXBytes = G::TILE_ELEMS * sizeof(T);
+  constexpr uint32_t kXBytesAl = (kXBytes + 127) & ~127u;
+  constexpr uint32_t kGBytes = G::TH * G::TW * CVB * 8 * sizeof(T);
+  extern __shared__ __align__(128) uint8_t dw_smem[];   // no integer casts: keeps the shared address space (LDS, not LD)
+  DwRing ring = dw_ring_init(dw_smem, ns, stage_bytes);
+  float* s_bnbuf = reinterpret_cast<float*>(ring.full + ns + (ns & 1));
   const int tid = threadIdx.x;
-  const int PLn = kDwThreads / CVB;
   const int cvl = tid % CVB, pl = tid / CVB;
-  const bool active = pl < PLn;
+  const bool active = pl < G::PLn;
   const int cv0 = blockIdx.y * CVB;
-  const float* s_bn = dw_stage_bn(s_bnbuf, scale, shift, cv0, CVB);
+  const float* s_bn = dw_stage_bn(s_bnbuf, scale, shift, cv0, CVB * 8);
   float acc[9][8];
 #pragma unroll
   for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[tp][i] = 0.f;
-  const int items = g.TH * g.TW;
-  for (int64_t t = blockIdx.x; t < g.n_tiles; t += gridDim.x) {
-    const int tw = (int)(t % g.tiles_w);
-    const int64_t t2 = t / g.tiles_w;
-    const int th = (int)(t2 % g.tiles_h);
-    const int n = (int)(t2 / g.tiles_h);
-    const int oh0 = th * g.TH, ow0 = tw * g.TW;
-    __syncthreads();
+    for (int k = 0; k < 8; ++k) acc[tp][k] = 0.f;
+  const int my_tiles = (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto issue = [&](int i) {
+    int n, th, tw;
+    dw_tile_coords(blockIdx.x + i * gridDim.x, g, n, th, tw);
+    const int slot = i % ns;
+    uint8_t* buf = ring.bufs + (size_t)slot * stage_bytes;
+    mbar_arrive_expect_tx(&ring.full[slot], kXBytes + kGBytes);
+    tma_load_4d(buf, &tmX, cv0 * 8, tw * G::TW * S - 1, th * G::TH * S - 1, n, &ring.full[slot]);
+    // out-of-image outputs arrive as zero gradients: no bounds checks in the arithmetic
+    tma_load_4d(buf + kXBytesAl, &tmDY, cv0 * 8, tw * G::TW, th * G::TH, n, &ring.full[slot]);
+  };
+  __syncthreads();
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int i = 0; i < ns && i < my_tiles; ++i) issue(i);
+  }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int i = 0; i < my_tiles; ++i) {
+    int n, th, tw;
+    dw_tile_coords(blockIdx.x + i * gridDim.x, g, n, th, tw);
+    T* tile = reinterpret_cast<T*>(ring.bufs + (size_t)slot * stage_bytes);
+    const T* gt = reinterpret_cast<const T*>(ring.bufs + (size_t)slot * stage_bytes + kXBytesAl);
+    mbar_wait(&ring.full[slot], phase);
+    if (s_bn) {
+      if (active)
+        dw_normalize<T, G::IH, G::IW, CVB>(tile, th * G::TH * S - 1, tw * G::TW * S - 1, H, W, s_bn, act, cvl, pl);
+      __syncthreads();
+    }
     if (active) {
-      dw_stage<T>(tile, x, ldx, n, oh0 * STRIDE - 1, ow0 * STRIDE - 1, g.IH, g.IW, H, W, cv0, CVB, s_bn, act, cvl, pl,
-                  PLn);
-      dw_stage<T>(gt, dy, lddy, n, oh0, ow0, g.TH, g.TW, Ho, Wo, cv0, CVB, nullptr, 0, cvl, pl, PLn);
+#pragma unroll 1
+      for (int it = pl; it < G::ITEMS; it += G::PLn) {
+        const int r = it / G::STRIPS, sw = it - r * G::STRIPS;
+        f8 gv[TWP];
+#pragma unroll
+        for (int j = 0; j < TWP; ++j) gv[j] = load8<T>(gt + ((r * G::TW + sw * TWP + j) * CVB + cvl) * 8);
+        const T* tp0 = tile + ((r * S * G::IW + sw * TWP * S) * CVB + cvl) * 8;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int c = 0; c < NI; ++c) {
+            const f8 v = load8<T>(tp0 + (kh * G::IW + c) * CVB * 8);
+#pragma unroll
+            for (int j = 0; j < TWP; ++j) {
+              const int kw = c - j * S;
+              if (kw >= 0 && kw < 3) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[kh * 3 + kw][k] = fmaf(v.v[k], gv[j].v[k], acc[kh * 3 + kw][k]);
+              }
+            }
+          }
+      }
     }
     __syncthreads();
-    if (!active) continue;
-    for (int it = pl; it < items; it += PLn) {
-      const int r = it / g.TW, c = it - r * g.TW;
-      // out-of-image outputs were staged as zero gradients: no branch needed
-      const f8 gv = load8<T>(gt + ((size_t)it * CVB + cvl) * 8);
-      const T* tp0 = tile + ((size_t)(r * STRIDE * g.IW + c * STRIDE) * CVB + cvl) * 8;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const f8 v = load8<T>(tp0 + (size_t)(kh * g.IW + kw) * CVB * 8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[kh * 3 + kw][i] = fmaf(v.v[i], gv.v[i], acc[kh * 3 + kw][i]);
-        }
+    if (tid == 0 && i + ns < my_tiles) {
+      fence_proxy_async();
+      issue(i + ns);
+    }
+    if (++slot == ns) {
+      slot = 0;
+      phase ^= 1;
     }
   }
   // deterministic block reduction, one tap at a time through [pl][cvl][8] floats (8 KB)
-  float* red = reinterpret_cast<float*>(dw_smem);
+  float* red = reinterpret_cast<float*>(ring.bufs);
   float* row = partial + (int64_t)blockIdx.x * C * 9;
 #pragma unroll
   for (int tp = 0; tp < 9; ++tp) {
     __syncthreads();
     if (active) {
-      float* mine = red + ((size_t)pl * CVB + cvl) * 8;
+      float* mine = red + (pl * CVB + cvl) * 8;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mine[i] = acc[tp][i];
+      for (int k = 0; k < 8; ++k) mine[k] = acc[tp][k];
     }
     __syncthreads();
     for (int o = tid; o < CVB * 8; o += kDwThreads) {
-      float s = 0.f;
-      for (int j = 0; j < PLn; ++j) s += red[(size_t)j * CVB * 8 + o];
-      row[(cv0 * 8 + o) * 9 + tp] = s;
+      float sv = 0.f;
+      for (int j = 0; j < G::PLn; ++j) sv += red[j * CVB * 8 + o];
+      row[(cv0 * 8 + o) * 9 + tp] = sv;
     }
   }
 }
@@ -417,6 +523,9 @@ dw_dgrad_generic_kernel(const T* __restrict__ dy, int lddy, const float* __restr
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
 template <typename K>
 static int set_smem(K kernel, size_t smem) {
   if (smem <= 48 * 1024) return SC_OK;
@@ -428,38 +537,164 @@ static int set_smem(K kernel, size_t smem) {
   return SC_OK;
 }
 
-static int pick_tw(int Wo, int twp) {
-  int tw = Wo >= 16 ? 16 : ((Wo + twp - 1) / twp) * twp;
-  return tw;
+// channel-block widths with a compiled kernel, widest first
+static int pick_cvb(int CV) {
+  static const int opts[] = {8, 6, 4, 3, 2, 1};
+  for (int d : opts)
+    if (CV % d == 0) return d;
+  return 1;
 }
+
+static int dw_grid_x(const DwTiles& g, int n_cb, int ctas_per_sm, int max_rows) {
+  int64_t cap = ((int64_t)kNumSMs * ctas_per_sm + n_cb - 1) / n_cb;
+  if (cap < 1) cap = 1;
+  if (cap > max_rows) cap = max_rows;
+  return (int)(g.n_tiles < cap ? g.n_tiles : cap);
+}
+
+static bool dw_tiles(int N, int Ho, int Wo, int TH, int TW, DwTiles* g) {
+  g->tiles_h = (Ho + TH - 1) / TH;
+  g->tiles_w = (Wo + TW - 1) / TW;
+  int64_t n = (int64_t)N * g->tiles_h * g->tiles_w;
+  if (n > INT32_MAX) return false;
+  g->n_tiles = (int)n;
+  return true;
+}
+
+// ring depth: as many tiles in flight as fit a per-CTA budget that keeps `ctas` CTAs resident per SM
+static int dw_ring_depth(size_t stage_bytes, size_t extra, int ctas) {
+  const size_t budget = (size_t)(227 * 1024) / ctas - 1024 - extra - 256;
+  int ns = (int)(budget / stage_bytes);
+  if (ns > 4) ns = 4;
+  return ns;
+}
+
+template <typename T, int S, int CVB>
+static int launch_fprop_cvb(const T* x, int ldx, const float* scale, const float* shift, int act, const float* w,
+                            int mirror, T* y, int ldy, double* stats, int* stats_rows_host, int N, int H, int W, int C,
+                            cudaStream_t st) {
+  using G = DwGeo<S, CVB, (S == 1 ? 4 : 2)>;
+  const int Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+  DwTiles g;
+  if (!dw_tiles(N, Ho, Wo, G::TH, G::TW, &g)) return SC_ERR_BAD_ARG;
+  const int n_cb = (C / 8) / CVB;
+  size_t stage = ((size_t)G::TILE_ELEMS * sizeof(T) + 127) & ~(size_t)127;
+  const size_t extra = (size_t)11 * CVB * 8 * sizeof(float) + 64;
+  int ctas = DW_FPROP_CTAS;
+  int ns = dw_ring_depth(stage, extra, ctas);
+  while (ns < 2 && ctas > 1) ns = dw_ring_depth(stage, extra, --ctas);
+  if (ns < 1) return SC_ERR_UNSUPPORTED;
+  if ((size_t)ns * stage < (size_t)kDwThreads * 16 * sizeof(float)) stage = (size_t)kDwThreads * 16 * sizeof(float);
+  const int gx = dw_grid_x(g, n_cb, ctas, stats ? SC_BN_MAX_PARTIALS : 1 << 30);
+  const size_t smem = 128 + (size_t)ns * stage + extra;
+  if (stats_rows_host) *stats_rows_host = gx;
+  CUtensorMap tmX;
+  if (!encode_nhwc_plain(&tmX, x, (int)sizeof(T), C, W, H, N, ldx, CVB * 8, G::IW, G::IH)) return SC_ERR_NO_DEVICE;
+  int rc = set_smem(dw_fprop_kernel<T, S, CVB>, smem);
+  if (rc != SC_OK) return rc;
+  dw_fprop_kernel<T, S, CVB><<<dim3(gx, n_cb), kDwThreads, smem, st>>>(tmX, scale, shift, act, w, mirror, y, ldy, stats, H,
+                                                                       W, C, Ho, Wo, g, ns, (int)stage);
+  return check_launch();
+}
+
+template <typename T, int CVB>
+static int launch_dgrad_s2_cvb(const T* dy, int lddy, const float* w, T* dx, int lddx, int N, int H, int W, int C,
+                               cudaStream_t st) {
+  using G = DwGeoD2<CVB>;
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  DwTiles g;
+  if (!dw_tiles(N, Ho, Wo, G::TH, G::TW, &g)) return SC_ERR_BAD_ARG;
+  const int n_cb = (C / 8) / CVB;
+  const size_t stage = ((size_t)G::TILE_ELEMS * sizeof(T) + 127) & ~(size_t)127;
+  const size_t extra = (size_t)9 * CVB * 8 * sizeof(float) + 64;
+  int ctas = 3;
+  int ns = dw_ring_depth(stage, extra, ctas);
+  while (ns < 2 && ctas > 1) ns = dw_ring_depth(stage, extra, --ctas);
+  if (ns < 1) return SC_ERR_UNSUPPORTED;
+  const int gx = dw_grid_x(g, n_cb, ctas, 1 << 30);
+  const size_t smem = 128 + (size_t)ns * stage + extra;
+  CUtensorMap tmDY;
+  if (!encode_nhwc_plain(&tmDY, dy, (int)sizeof(T), C, Wo, Ho, N, lddy, CVB * 8, G::IW, G::IH)) return SC_ERR_NO_DEVICE;
+  int rc = set_smem(dw_dgrad_s2_kernel<T, CVB>, smem);
+  if (rc != SC_OK) return rc;
+  dw_dgrad_s2_kernel<T, CVB><<<dim3(gx, n_cb), kDwThreads, smem, st>>>(tmDY, w, dx, lddx, H, W, C, g, ns, (int)stage);
+  return check_launch();
+}
+
+template <typename T, int S, int CVB>
+static int launch_wgrad_cvb(const T* x, int ldx, const float* scale, const float* shift, int act, const T* dy, int lddy,
+                            float* workspace, int* rows, int N, int H, int W, int C, cudaStream_t st) {
+  using G = DwGeo<S, CVB, 2>;
+  const int Ho = (H - 1) / S + 1, Wo = (W - 1) / S + 1;
+  DwTiles g;
+  if (!dw_tiles(N, Ho, Wo, G::TH, G::TW, &g)) return SC_ERR_BAD_ARG;
+  const int n_cb = (C / 8) / CVB;
+  const size_t xal = ((size_t)G::TILE_ELEMS * sizeof(T) + 127) & ~(size_t)127;
+  const size_t stage = xal + (((size_t)G::TH * G::TW * CVB * 8 * sizeof(T) + 127) & ~(size_t)127);
+  const size_t extra = (size_t)2 * CVB * 8 * sizeof(float) + 64;
+  int ctas = 2;
+  int ns = dw_ring_depth(stage, extra, ctas);
+  while (ns < 2 && ctas > 1) ns = dw_ring_depth(stage, extra, --ctas);
+  if (ns < 1) return SC_ERR_UNSUPPORTED;
+  const int gx = dw_grid_x(g, n_cb, ctas, kDwMaxRows);
+  const size_t smem = 128 + (size_t)ns * stage + extra;     // ns*stage >= 8 KB reduction scratch
+  *rows = gx;
+  CUtensorMap tmX, tmDY;
+  if (!encode_nhwc_plain(&tmX, x, (int)sizeof(T), C, W, H, N, ldx, CVB * 8, G::IW, G::IH) ||
+      !encode_nhwc_plain(&tmDY, dy, (int)sizeof(T), C, Wo, Ho, N, lddy, CVB * 8, G::TW, G::TH))
+    return SC_ERR_NO_DEVICE;
+  int rc = set_smem(dw_wgrad_kernel<T, S, CVB>, smem);
+  if (rc != SC_OK) return rc;
+  dw_wgrad_kernel<T, S, CVB><<<dim3(gx, n_cb), kDwThreads, smem, st>>>(tmX, tmDY, scale, shift, act, workspace, H, W, C, g,
+                                                                       ns, (int)stage);
+  return check_launch();
+}
+
+#define DW_DISPATCH_CVB(cvb, ...)                            \
+  switch (cvb) {                                             \
+    case 8: { constexpr int CVB = 8; __VA_ARGS__; } break;   \
+    case 6: { constexpr int CVB = 6; __VA_ARGS__; } break;   \
+    case 4: { constexpr int CVB = 4; __VA_ARGS__; } break;   \
+    case 3: { constexpr int CVB = 3; __VA_ARGS__; } break;   \
+    case 2: { constexpr int CVB = 2; __VA_ARGS__; } break;   \
+    default: { constexpr int CVB = 1; __VA_ARGS__; } break;  \
+  }
 
 template <typename T>
 static int launch_fprop(const T* x, int ldx, const float* scale, const float* shift, int act, const float* w,
                         int mirror, T* y, int ldy, double* stats, int* stats_rows_host, int N, int H, int W, int C,
                         int stride, cudaStream_t st) {
-  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
-  const int twp = stride == 1 ? 4 : 2;
-  const int thm = stride == 1 ? 8 : 4;                 // stride 2 stages a (2*TH+1) x (2*TW+1) tile: keep it small
-  const int tw = pick_tw(Wo, twp), th = Ho >= thm ? thm : Ho;
-  DwPlan g = dw_plan(N, Ho, Wo, C / 8, th, tw, (th - 1) * stride + 3, (tw - 1) * stride + 3, 6,
-                     stats ? SC_BN_MAX_PARTIALS : 1 << 30);
-  size_t tile_bytes = (size_t)g.IH * g.IW * g.CVB * 8 * sizeof(T);
-  if (stats && tile_bytes < (size_t)kDwThreads * 16 * sizeof(float)) tile_bytes = (size_t)kDwThreads * 16 * sizeof(float);
-  const size_t smem = (size_t)11 * g.CVB * 8 * sizeof(float) + tile_bytes;
-  if (smem > 200 * 1024) return SC_ERR_UNSUPPORTED;
-  if (stats_rows_host) *stats_rows_host = g.grid_x;
-  dim3 grid(g.grid_x, g.n_cb);
-  int rc;
+  const int cvb = pick_cvb(C / 8);
   if (stride == 1) {
-    if ((rc = set_smem(dw_fprop_kernel<T, 1, 4>, smem)) != SC_OK) return rc;
-    dw_fprop_kernel<T, 1, 4><<<grid, kDwThreads, smem, st>>>(x, ldx, scale, shift, act, w, mirror, y, ldy, stats, H, W, C,
-                                                             Ho, Wo, g);
+    DW_DISPATCH_CVB(cvb, return (launch_fprop_cvb<T, 1, CVB>(x, ldx, scale, shift, act, w, mirror, y, ldy, stats,
+                                                              stats_rows_host, N, H, W, C, st)));
   } else {
-    if ((rc = set_smem(dw_fprop_kernel<T, 2, 2>, smem)) != SC_OK) return rc;
-    dw_fprop_kernel<T, 2, 2><<<grid, kDwThreads, smem, st>>>(x, ldx, scale, shift, act, w, mirror, y, ldy, stats, H, W, C,
-                                                             Ho, Wo, g);
+    DW_DISPATCH_CVB(cvb, return (launch_fprop_cvb<T, 2, CVB>(x, ldx, scale, shift, act, w, mirror, y, ldy, stats,
+                                                              stats_rows_host, N, H, W, C, st)));
   }
-  return check_launch();
+  return SC_ERR_BAD_ARG;
+}
+
+template <typename T>
+static int launch_dgrad_s2(const T* dy, int lddy, const float* w, T* dx, int lddx, int N, int H, int W, int C,
+                           cudaStream_t st) {
+  const int cvb = pick_cvb(C / 8);
+  DW_DISPATCH_CVB(cvb, return (launch_dgrad_s2_cvb<T, CVB>(dy, lddy, w, dx, lddx, N, H, W, C, st)));
+  return SC_ERR_BAD_ARG;
+}
+
+template <typename T>
+static int launch_wgrad(const T* x, int ldx, const float* scale, const float* shift, int act, const T* dy, int lddy,
+                        float* workspace, int* rows, int N, int H, int W, int C, int stride, cudaStream_t st) {
+  const int cvb = pick_cvb(C / 8);
+  if (stride == 1) {
+    DW_DISPATCH_CVB(cvb, return (launch_wgrad_cvb<T, 1, CVB>(x, ldx, scale, shift, act, dy, lddy, workspace, rows, N, H,
+                                                              W, C, st)));
+  } else {
+    DW_DISPATCH_CVB(cvb, return (launch_wgrad_cvb<T, 2, CVB>(x, ldx, scale, shift, act, dy, lddy, workspace, rows, N, H,
+                                                              W, C, st)));
+  }
+  return SC_ERR_BAD_ARG;
 }
 
 }  // namespace
@@ -484,24 +719,16 @@ extern "C" int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* d
     SC_DISPATCH_DTYPE(dtype, return launch_fprop<T>((const T*)dy, lddy, nullptr, nullptr, SC_ACT_NONE, w, 1, (T*)dx,
                                                     lddx, nullptr, nullptr, N, H, W, C, 1, st));
   }
-  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   if ((H | W) & 1) {
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     int64_t total = (int64_t)N * H * W * (C / 8);
     int64_t b = (total + 255) / 256, cap = (int64_t)kNumSMs * 8;
     SC_DISPATCH_DTYPE(dtype, (dw_dgrad_generic_kernel<T><<<(int)(b < cap ? b : cap), 256, 0, st>>>(
                                  (const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C, stride, Ho, Wo)));
     return check_launch();
   }
-  const int tw = Wo >= 16 ? 16 : Wo, th = Ho >= 8 ? 8 : Ho;
-  DwPlan g = dw_plan(N, Ho, Wo, C / 8, th, tw, th + 1, tw + 1, 6, 1 << 30);
-  dim3 grid(g.grid_x, g.n_cb);
-  SC_DISPATCH_DTYPE(dtype, {
-    const size_t smem = (size_t)9 * g.CVB * 8 * sizeof(float) + (size_t)g.IH * g.IW * g.CVB * 8 * sizeof(T);
-    int rc = set_smem(dw_dgrad_s2_kernel<T>, smem);
-    if (rc != SC_OK) return rc;
-    dw_dgrad_s2_kernel<T><<<grid, kDwThreads, smem, st>>>((const T*)dy, lddy, w, (T*)dx, lddx, H, W, C, Ho, Wo, g);
-  });
-  return check_launch();
+  SC_DISPATCH_DTYPE(dtype, return launch_dgrad_s2<T>((const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C, st));
+  return SC_ERR_BAD_ARG;
 }
 
 extern "C" int64_t sc_dwconv_wgrad_workspace_bytes(int C) { return (int64_t)kDwMaxRows * C * 9 * sizeof(float); }
@@ -511,29 +738,11 @@ extern "C" int sc_dwconv_wgrad(const void* x, int ldx, const float* scale, const
                                int stride, int dtype, void* stream) {
   if (!x || !dy || !dw || !workspace || C % 8 || ldx % 8 || lddy % 8 || (stride != 1 && stride != 2) || N <= 0)
     return SC_ERR_BAD_ARG;
-  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   cudaStream_t st = (cudaStream_t)stream;
-  const int thm = stride == 1 ? 8 : 4;
-  const int tw = Wo >= 16 ? 16 : Wo, th = Ho >= thm ? thm : Ho;
-  DwPlan g = dw_plan(N, Ho, Wo, C / 8, th, tw, (th - 1) * stride + 3, (tw - 1) * stride + 3, 2, kDwMaxRows);
-  dim3 grid(g.grid_x, g.n_cb);
-  SC_DISPATCH_DTYPE(dtype, {
-    size_t smem = (size_t)2 * g.CVB * 8 * sizeof(float) + ((size_t)g.IH * g.IW + (size_t)g.TH * g.TW) * g.CVB * 8 * sizeof(T);
-    if (smem < (size_t)kDwThreads * 8 * sizeof(float)) smem = (size_t)kDwThreads * 8 * sizeof(float);
-    if (smem > 110 * 1024) return SC_ERR_UNSUPPORTED;
-    int rc;
-    if (stride == 1) {
-      if ((rc = set_smem(dw_wgrad_kernel<T, 1>, smem)) != SC_OK) return rc;
-      dw_wgrad_kernel<T, 1><<<grid, kDwThreads, smem, st>>>((const T*)x, ldx, scale, shift, act, (const T*)dy, lddy,
-                                                            workspace, H, W, C, Ho, Wo, g);
-    } else {
-      if ((rc = set_smem(dw_wgrad_kernel<T, 2>, smem)) != SC_OK) return rc;
-      dw_wgrad_kernel<T, 2><<<grid, kDwThreads, smem, st>>>((const T*)x, ldx, scale, shift, act, (const T*)dy, lddy,
-                                                            workspace, H, W, C, Ho, Wo, g);
-    }
-  });
-  int rc = check_launch();
+  int rows = 0, rc = SC_ERR_BAD_ARG;
+  SC_DISPATCH_DTYPE(dtype, rc = launch_wgrad<T>((const T*)x, ldx, scale, shift, act, (const T*)dy, lddy, workspace, &rows,
+                                                N, H, W, C, stride, st));
   if (rc != SC_OK) return rc;
-  dw_wgrad_sum_kernel<<<(C * 9 + 31) / 32, dim3(32, 32), 0, st>>>(workspace, g.grid_x, C * 9, dw);
+  dw_wgrad_sum_kernel<<<(C * 9 + 31) / 32, dim3(32, 32), 0, st>>>(workspace, rows, C * 9, dw);
   return check_launch();
 }
