@@ -208,6 +208,15 @@ int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void* y, int ld
 int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw,
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, void* stream);
 
+/* Thin-layer variant for 3x3 / stride 1 / pad 1 (decoder blocks 2-4, fprop and dgrad): the 18x10 input halo
+ * patch of a 16x8 pixel tile is staged ONCE (9x less L2->SM traffic than one shifted box per tap) and all nine
+ * taps' weights stay resident in shared memory.  Packed weights: bf16 [Cout][9][sc_tc_halo_cin_pad(Cin)]
+ * (sc_tc_pack_weights with cin_pad = that value).  Any H, W; Cin % 8 == 0; Cout % 16 == 0, Cout <= 128. */
+int sc_tc_halo_cin_pad(int Cin);
+int sc_tc_halo_supported(int Cin, int Cout);
+int sc_tc_conv3x3_halo(const void* x, int ldx, const void* w_bf16, void* y, int ldy, double* stats,
+                       int* stats_rows_host, int N, int H, int W, int Cin, int Cout, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

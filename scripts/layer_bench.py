@@ -68,7 +68,18 @@ for name, cin, cout, k, div in layers:
         "wgrad": lambda i: call("sc_tc_conv_wgrad", xs[i % NB].data_ptr(), ldx, ys[i % NB].data_ptr(), cout, dw.data_ptr(),
                                 B, H, W, cin, cout, k, k, stride, st),
     }
-    for op in a.ops.split(","):
+    halo = k == 3 and stride == 1 and lib.sc_tc_halo_supported(cin, cout) and lib.sc_tc_halo_supported(cout, cin)
+    if halo:
+        hp, hp2 = lib.sc_tc_halo_cin_pad(cin), lib.sc_tc_halo_cin_pad(cout)
+        wbh = torch.empty(cout * 9 * hp, dtype=torch.bfloat16, device=dev)
+        call("sc_tc_pack_weights", w.data_ptr(), wbh.data_ptr(), cout, cin, 3, 3, 0, hp, cout, st)
+        wth = torch.empty(cin * 9 * hp2, dtype=torch.bfloat16, device=dev)
+        call("sc_tc_pack_weights", w.data_ptr(), wth.data_ptr(), cout, cin, 3, 3, 1, cin, hp2, st)
+        ops["fprop_halo"] = lambda i: call("sc_tc_conv3x3_halo", xs[i % NB].data_ptr(), ldx, wbh.data_ptr(), ys[i % NB].data_ptr(),
+                                           cout, part.data_ptr(), ctypes.byref(n), B, H, W, cin, cout, 0, st)
+        ops["dgrad_halo"] = lambda i: call("sc_tc_conv3x3_halo", ys[i % NB].data_ptr(), cout, wth.data_ptr(), xs[i % NB].data_ptr(),
+                                           ldx, 0, 0, B, H, W, cout, cin, 0, st)
+    for op in a.ops.split(",") + (["fprop_halo", "dgrad_halo"] if halo else []):
         if op == "dgrad" and (stride != 1 or cin % 8): continue
         us = timeit(ops[op])
         tot[op] = tot.get(op, 0) + us

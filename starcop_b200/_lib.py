@@ -52,6 +52,9 @@ SIGNATURES = {
     "sc_tc_pack_weights": [P, P, I, I, I, I, I, I, I, P],
     "sc_tc_cin_pad": [I],
     "sc_tc_conv_fprop": [P, I, P, P, I, P, P, I, I, I, I, I, I, I, I, I, P],
+    "sc_tc_halo_cin_pad": [I],
+    "sc_tc_halo_supported": [I, I],
+    "sc_tc_conv3x3_halo": [P, I, P, P, I, P, P, I, I, I, I, I, I, P],
     "sc_tc_conv_wgrad": [P, I, P, I, P, I, I, I, I, I, I, I, I, P],
 }
 _RESTYPES = {"sc_last_cuda_error": ctypes.c_char_p, "sc_mag1c_smem_bytes": c_int64, "sc_bn_partials_bytes": c_int64, "sc_mlr_workspace_bytes": c_int64, "sc_dwconv_wgrad_workspace_bytes": c_int64,

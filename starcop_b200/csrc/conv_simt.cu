@@ -130,11 +130,20 @@ conv_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ wp
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+  // Two-level summation: each BK-long chunk is accumulated in `part` and folded into `acc` once, so
+  // the rounding error grows like sqrt(BK) + sqrt(K/BK) instead of sqrt(K) (K reaches 12384 in the
+  // decoder).  This is the fp32 PARITY path: its noise on the zero-true-gradient parameters (anything
+  // feeding a BatchNorm) is compared with PyTorch's blocked CPU kernels by the tests.
+  float part[TM][TN];
   load_tiles(0);
   for (int k0 = 0; k0 < K; k0 += BK) {
     store_tiles();
     __syncthreads();
     if (k0 + BK < K) load_tiles(k0 + BK);
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[TM], b[TN];
@@ -151,8 +160,12 @@ conv_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ wp
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) part[i][j] = fmaf(a[i], b[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] += part[i][j];
     __syncthreads();
   }
 
@@ -259,6 +272,12 @@ conv_wgrad_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, in
     *reinterpret_cast<float4*>(&As[lr][lc]) = make_float4(a[0], a[1], a[2], a[3]);
     *reinterpret_cast<float4*>(&Bs[lr][lc]) = make_float4(b[0], b[1], b[2], b[3]);
     __syncthreads();
+    // two-level summation (see conv_fprop_kernel): 16-pixel chunks folded into the running sums
+    float part[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * TM]);
@@ -267,8 +286,12 @@ conv_wgrad_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, in
 #pragma unroll
       for (int i = 0; i < TM; ++i)
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
+        for (int j = 0; j < TN; ++j) part[i][j] = fmaf(aa[i], bb[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+      for (int j = 0; j < TN; ++j) acc[i][j] += part[i][j];
   }
   const int KK = KH * KW;
 #pragma unroll

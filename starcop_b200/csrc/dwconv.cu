@@ -44,6 +44,9 @@ struct DwGeo {
   static constexpr int TILE_ELEMS = IH * IW * CVB * 8;
 };
 
+template <typename T> struct StatAcc { using type = float; };
+template <> struct StatAcc<float> { using type = double; };
+
 struct DwTiles {
   int tiles_h, tiles_w;
   int n_tiles;           // N * tiles_h * tiles_w
@@ -136,9 +139,11 @@ dw_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict
     ws[i] = w[(cv0 * 8 + c) * 9 + (mirror ? 8 - tap : tap)];
   }
   const float* s_bn = dw_stage_bn(ws + 9 * CVB * 8, scale, shift, cv0, CVB * 8);
-  float ssum[8], ssq[8];
+  // per-thread statistics: fp32 in the bf16 throughput mode, fp64 in the fp32 parity mode
+  using StatT = typename StatAcc<T>::type;
+  StatT ssum[8], ssq[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ssum[i] = ssq[i] = 0.f;
+  for (int i = 0; i < 8; ++i) ssum[i] = ssq[i] = (StatT)0;
   const float* wsc = ws + cvl * 8;
   const int my_tiles = (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   auto issue = [&](int i) {     // thread 0: TMA the CTA's i-th tile into slot i % ns
@@ -209,9 +214,9 @@ dw_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict
             // statistics of the STORED (storage-precision) values, like the separate pass would see them
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const float sv = to_f<T>(from_f<T>(o.v[k]));
+              const StatT sv = (StatT)to_f<T>(from_f<T>(o.v[k]));
               ssum[k] += sv;
-              ssq[k] = fmaf(sv, sv, ssq[k]);
+              ssq[k] += sv * sv;
             }
           }
         }
@@ -229,9 +234,9 @@ dw_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict
   }
   if (stats) {
     // deterministic block reduction: stage [pl][cvl][16] floats, then 16*CVB threads sum over pl in fixed order
-    float* red = reinterpret_cast<float*>(ring.bufs);          // >= 256*16*4 = 16 KB guaranteed by the launcher
+    StatT* red = reinterpret_cast<StatT*>(ring.bufs);          // >= 256*16*8 = 32 KB guaranteed by the launcher
     if (active) {
-      float* mine = red + (pl * CVB + cvl) * 16;
+      StatT* mine = red + (pl * CVB + cvl) * 16;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         mine[k] = ssum[k];
@@ -584,7 +589,7 @@ static int launch_fprop_cvb(const T* x, int ldx, const float* scale, const float
   int ns = dw_ring_depth(stage, extra, ctas);
   while (ns < 2 && ctas > 1) ns = dw_ring_depth(stage, extra, --ctas);
   if (ns < 1) return SC_ERR_UNSUPPORTED;
-  if ((size_t)ns * stage < (size_t)kDwThreads * 16 * sizeof(float)) stage = (size_t)kDwThreads * 16 * sizeof(float);
+  if ((size_t)ns * stage < (size_t)kDwThreads * 16 * sizeof(double)) stage = (size_t)kDwThreads * 16 * sizeof(double);
   const int gx = dw_grid_x(g, n_cb, ctas, stats ? SC_BN_MAX_PARTIALS : 1 << 30);
   const size_t smem = 128 + (size_t)ns * stage + extra;
   if (stats_rows_host) *stats_rows_host = gx;

@@ -8,6 +8,7 @@ nearest-x2 upsample + concat fused into the producer's store, skip features writ
 into the decoder's concat buffers, gradients routed through channel-slice views instead of copies.
 """
 import ctypes
+import os
 
 import torch
 
@@ -95,6 +96,7 @@ class UNetEngine:
         self.record = False
         self.stream = 0
         self.use_tc = self.dtype == SC_BF16 and bool(_lib.load().sc_tc_supported())
+        self.use_halo = os.environ.get("STARCOP_NO_HALO", "") == ""
 
     # ------------------------------------------------------------------ memory
     def begin_step(self):
@@ -196,6 +198,13 @@ class UNetEngine:
         return (self.dtype == SC_BF16 and self.use_tc and (stride == 1 or (stride == 2 and k == 3)) and k in (1, 3)
                 and cout % 8 == 0 and wo % 16 == 0 and ho % 8 == 0 and x.ld % 8 == 0)
 
+    def _halo_ok(self, x, cin, cout, k, stride):
+        """thin 3x3 layers (decoder blocks 2-4): one staged halo patch per tile + resident weights (conv_tc_halo.cu)"""
+        # measured on B200 (profiles/r01_layer_bench.txt): it wins where both channel counts are <= 32
+        # (decoder blocks 3.conv2, 4.conv1, 4.conv2: 1.1x ... 3.4x); wider layers stay on the per-tap kernel
+        return (self.use_halo and self.dtype == SC_BF16 and self.use_tc and k == 3 and stride == 1 and x.ld % 8 == 0
+                and cin <= 32 and cout <= 32 and bool(_lib.load().sc_tc_halo_supported(cin, cout)))
+
     def _dense_fprop(self, x, wname, k, stride, want_stats=False):
         """-> (y, sums): sums is the fp64 [2*Cout] statistics buffer when the conv epilogue produced it."""
         w = self.p[wname]
@@ -204,6 +213,15 @@ class UNetEngine:
         pad = k // 2
         Ho, Wo = (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1
         y = self.new(x.N, Ho, Wo, cout)
+        if self._halo_ok(x, cin, cout, k, stride):
+            lib = _lib.load()
+            cpad = lib.sc_tc_halo_cin_pad(cin)
+            wb = self.arena.alloc(cout * 9 * cpad * 2)
+            call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, 3, 3, 0, cpad, cout, self.stream)
+            part, n = (self._partials(cout), ctypes.c_int(0)) if want_stats else (0, ctypes.c_int(0))
+            call("sc_tc_conv3x3_halo", x.ptr, x.ld, wb, y.ptr, y.ld, part, ctypes.byref(n), x.N, x.H, x.W, cin, cout, 0,
+                 self.stream)
+            return y, ((part, n.value) if want_stats else None)
         if self._tc_ok(x, cin, cout, k, stride):
             cpad = _lib.load().sc_tc_cin_pad(cin)
             wb = self.arena.alloc(cout * k * k * cpad * 2)
@@ -235,7 +253,14 @@ class UNetEngine:
         if need_dx:
             assert stride == 1
             dst, acc = self._grad_dst(x)
-            if tc:
+            if tc and self._halo_ok(dy, cout, cin, k, 1) and dst.ld % 8 == 0:
+                lib = _lib.load()
+                cpad = lib.sc_tc_halo_cin_pad(cout)
+                wb = self.arena.alloc(cin * 9 * cpad * 2)
+                call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, 3, 3, 1, cin, cpad, self.stream)
+                call("sc_tc_conv3x3_halo", dy.ptr, dy.ld, wb, dst.ptr, dst.ld, 0, 0, dy.N, dy.H, dy.W, cout, cin, acc,
+                     self.stream)
+            elif tc:
                 cpad = _lib.load().sc_tc_cin_pad(cout)          # dgrad conv: input channels = Cout
                 wb = self.arena.alloc(cin * k * k * cpad * 2)
                 call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, k, k, 1, cin, cpad, self.stream)

@@ -122,3 +122,64 @@ def test_tc_stem_stride2_fprop_and_wgrad():
     call("sc_tc_conv_wgrad", x8.data_ptr(), 8, dy.data_ptr(), Cout, dw.data_ptr(), N, H, W, Cin, Cout, k, k, 2, st())
     (gw,) = torch.autograd.grad(ref, wr, dy.float().permute(0, 3, 1, 2))
     assert (dw - gw).abs().max().item() <= 2e-3 * gw.abs().max().item()
+
+
+HALO_CASES = [  # N, H, W, Cin, Cout
+    (1, 16, 8, 16, 16),       # one tile, one K pair
+    (2, 32, 32, 32, 16),      # decoder block 4 conv1 geometry, several tiles
+    (2, 32, 24, 16, 32),      # its dgrad geometry
+    (3, 48, 40, 80, 32),      # decoder block 3 conv1: 5 K pairs, persistent loop over > 2 accumulator stages
+    (1, 20, 12, 24, 48),      # ragged tile edges (H % 16, W % 8 != 0) and a zero-filled half K pair (Cin % 16 != 0)
+    (2, 16, 16, 64, 64),      # decoder block 2 conv2: 72 KB of resident weights
+]
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", HALO_CASES)
+@pytest.mark.parametrize("with_stats", [False, True])
+def test_tc_halo_fprop(N, H, W, Cin, Cout, with_stats):
+    """thin-layer 3x3 kernel (one halo patch per tile, resident weights) against PyTorch on the same bf16 operands"""
+    import ctypes
+    lib = load()
+    assert lib.sc_tc_halo_supported(Cin, Cout) == 1
+    x, w = make(N, H, W, Cin, Cout, 3)
+    cpad = lib.sc_tc_halo_cin_pad(Cin)
+    wb = torch.empty(Cout * 9 * cpad, device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_pack_weights", w.data_ptr(), wb.data_ptr(), Cout, Cin, 3, 3, 0, cpad, Cout, st())
+    y = torch.full((N, H, W, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    part = torch.full((lib.sc_bn_partials_bytes(Cout) // 8,), float("nan"), dtype=torch.float64, device=DEV)
+    nrows = ctypes.c_int(0)
+    call("sc_tc_conv3x3_halo", x.data_ptr(), Cin, wb.data_ptr(), y.data_ptr(), Cout, part.data_ptr() if with_stats else 0,
+         ctypes.byref(nrows), N, H, W, Cin, Cout, 0, st())
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(y.float(), ref.to(torch.bfloat16).float(), rtol=1.6e-2, atol=1e-3)
+    if with_stats:
+        yf = y.double().reshape(-1, Cout)
+        stats = part[:nrows.value * 2 * Cout].view(nrows.value, 2 * Cout).sum(0)
+        assert torch.allclose(stats[:Cout], yf.sum(0), rtol=1e-4, atol=1e-2)
+        assert torch.allclose(stats[Cout:], (yf * yf).sum(0), rtol=1e-4, atol=1e-2)
+    # accumulate flag (gradient fan-in) and a channel-strided input / output (slices of a concat buffer)
+    xw = torch.zeros(N, H, W, Cin + 8, device=DEV, dtype=torch.bfloat16)
+    xw[..., 8:] = x
+    yw = torch.zeros(N, H, W, Cout + 16, device=DEV, dtype=torch.bfloat16)
+    yw[..., :Cout] = y
+    call("sc_tc_conv3x3_halo", xw.data_ptr() + 16, Cin + 8, wb.data_ptr(), yw.data_ptr(), Cout + 16, 0, 0, N, H, W, Cin, Cout,
+         1, st())
+    assert torch.allclose(yw[..., :Cout].float(), 2 * ref, rtol=3e-2, atol=4e-2)
+    assert float(yw[..., Cout:].abs().max()) == 0.0
+
+
+def test_tc_halo_dgrad_via_flipped_weights():
+    N, H, W, Cin, Cout = 2, 32, 32, 32, 16
+    lib = load()
+    x, w = make(N, H, W, Cin, Cout, 3)
+    dy = torch.randn(N, H, W, Cout, device=DEV).to(torch.bfloat16)
+    cpad = lib.sc_tc_halo_cin_pad(Cout)
+    wt = torch.empty(Cin * 9 * cpad, device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_pack_weights", w.data_ptr(), wt.data_ptr(), Cout, Cin, 3, 3, 1, Cin, cpad, st())
+    dx = torch.empty(N, H, W, Cin, device=DEV, dtype=torch.bfloat16)
+    call("sc_tc_conv3x3_halo", dy.data_ptr(), Cout, wt.data_ptr(), dx.data_ptr(), Cin, 0, 0, N, H, W, Cout, Cin, 0, st())
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.conv2d(xr, w.to(torch.bfloat16).float(), padding=1)
+    (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 3, 1, 2))
+    assert torch.allclose(dx.float(), gx.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
