@@ -542,32 +542,67 @@ class ModelModule(_Base):
         net.adam_step(self.lr if lr is None else lr, grad_scale=scale)
         return (loss_sum / n).float()[0]
 
-    def make_graphed_train_step(self, example_batch, grad_sync=None, warmup=2):
-        assert warmup >= 1, "at least one eager step must run first (it sizes the arenas and caches host state)"
+    def make_graphed_train_step(self, example_batch, grad_sync=None, warmup=2, double_buffer=False):
         """Capture train_step_fused into ONE CUDA graph (every buffer of the step comes from the static
         arenas, the Adam step counter and lr are device resident).  Returns ``step(batch) -> loss``:
         the batch is copied into the graph's static input buffers, the graph is replayed (~600 kernel
-        launches, one cudaGraphLaunch), the returned loss tensor is the graph's static output."""
+        launches, one cudaGraphLaunch), the returned loss tensor is the graph's static output.
+
+        ``double_buffer=True`` captures the step twice, over two sets of input buffers, and adds
+        ``step.prefetch(batch)``: the host-to-device copy of the NEXT batch runs on a copy stream while the
+        current step computes (what a pinned-memory DataLoader + ``non_blocking`` transfer does in the
+        reference loop); ``step()`` without arguments then consumes the oldest prefetched batch."""
+        assert warmup >= 1, "at least one eager step must run first (it sizes the arenas and caches host state)"
         dev = example_batch["input"].device
         keys = ["input", "output"] + (["weight_loss"] if self.reduction == "none" else [])
-        static = {k: torch.empty_like(example_batch[k], device=dev) for k in keys}
-        for k in keys:
-            static[k].copy_(example_batch[k])
+        nset = 2 if double_buffer else 1
+        statics = [{k: torch.empty_like(example_batch[k], device=dev) for k in keys} for _ in range(nset)]
+        for st in statics:
+            for k in keys:
+                st[k].copy_(example_batch[k])
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):                      # sizes the arenas, JITs nothing, warms NCCL
-                self.train_step_fused(static, grad_sync=grad_sync)
+                self.train_step_fused(statics[0], grad_sync=grad_sync)
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            loss = self.train_step_fused(static, grad_sync=grad_sync)
+        graphs, losses = [], []
+        for st in statics:                               # same arenas, same addresses: only the inputs differ
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                losses.append(self.train_step_fused(st, grad_sync=grad_sync))
+            graphs.append(g)
+        copy_stream = torch.cuda.Stream(device=dev) if double_buffer else None
+        ready = [torch.cuda.Event() for _ in range(nset)]      # H2D of the set finished (copy stream)
+        done = [torch.cuda.Event() for _ in range(nset)]       # the step that read the set finished (compute stream)
+        state = {"next_fill": 0, "pending": []}
 
-        def step(batch):
-            for k in keys:
-                static[k].copy_(batch[k], non_blocking=True)
-            graph.replay()
-            return loss
-        step.graph, step.static = graph, static
+        def prefetch(batch):
+            assert double_buffer, "make_graphed_train_step(..., double_buffer=True) is required for prefetch()"
+            assert len(state["pending"]) < nset, "both input buffer sets are full: call step() first"
+            s_ = state["next_fill"]
+            state["next_fill"] = (s_ + 1) % nset
+            copy_stream.wait_event(done[s_])             # the previous reader of this set has finished
+            with torch.cuda.stream(copy_stream):
+                for k in keys:
+                    statics[s_][k].copy_(batch[k], non_blocking=True)
+                ready[s_].record(copy_stream)
+            state["pending"].append(s_)
+
+        def step(batch=None):
+            cur = torch.cuda.current_stream(dev)
+            if batch is not None:
+                assert not state["pending"], "prefetched batches are waiting: call step() without a batch"
+                s_ = 0
+                for k in keys:
+                    statics[0][k].copy_(batch[k], non_blocking=True)
+            else:
+                assert state["pending"], "nothing prefetched: call step.prefetch(batch) first"
+                s_ = state["pending"].pop(0)
+                cur.wait_event(ready[s_])
+            graphs[s_].replay()
+            done[s_].record(cur)
+            return losses[s_]
+        step.graph, step.static, step.prefetch = graphs[0], statics[0], prefetch
         return step

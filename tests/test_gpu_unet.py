@@ -225,6 +225,33 @@ def test_graphed_train_step_matches_eager():
     assert int(m2.network._adam_state["step"].item()) == 4   # one eager warm-up + 3 replays (capture records, it does not execute)
 
 
+def test_graphed_step_prefetch_from_pinned_host_matches_direct_stepping():
+    """double-buffered inputs: the H2D copy of batch i+1 overlaps step i; losses equal the plain graphed loop"""
+    torch.manual_seed(7)
+    m1 = get_model(default_settings(pos_weight=1.0, compute_dtype="bf16"), None).to(DEV)
+    torch.manual_seed(7)
+    m2 = get_model(default_settings(pos_weight=1.0, compute_dtype="bf16"), None).to(DEV)
+    m1.train(); m2.train()
+    host = [synthetic.hyperstarcop_batch(2, size=64, seed=60 + s) for s in range(4)]
+    pinned = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in host]
+    s1 = m1.make_graphed_train_step(to_dev(host[0]), warmup=1)
+    s2 = m2.make_graphed_train_step(to_dev(host[0]), warmup=1, double_buffer=True)
+    l1 = [s1(to_dev(b)).item() for b in host]
+    l2 = []
+    s2.prefetch(pinned[0])
+    for i in range(4):
+        if i + 1 < 4:
+            s2.prefetch(pinned[i + 1])
+        l2.append(s2().item())
+    # both models took one eager warm-up step first: fp32-atomic summation order in the weight gradients lets
+    # the two runs drift by ~1e-4 (see the Adam test), a wrong or stale input buffer would be off by percents
+    for i, (a, b) in enumerate(zip(l1, l2)):
+        assert abs(a - b) <= 2e-3 * abs(a), (i, a, b)
+    assert max(l1) - min(l1) > 1e-2 * max(l1)        # the four batches really differ (so buffer mix-ups would show)
+    with pytest.raises(AssertionError):
+        s2()                                   # nothing prefetched
+
+
 def test_per_tile_validation_and_padded_predict():
     from oracle import loss_metrics as olm
     from starcop_b200 import tiling, validation
