@@ -12,6 +12,8 @@
 // memory.  All S x S arithmetic is fp64 (packed lower triangles), which is at least as accurate
 // as the reference's fp32/fp64 bmm of centred data.  Pixels are addressed through an index list,
 // which is how func_by_groups' gather / scatter (mag1c.py:161-172) is expressed on the device.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace sc;
@@ -319,6 +321,361 @@ mag1c_kernel(const TS* __restrict__ x, int64_t pixel_stride, const int32_t* __re
   if (tid == 0 && !ok && status) atomicAdd(status, 1);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Group-RESIDENT fast path (fp32 radiance, alpha = 0, <= 512 pixels per group: the AVIRIS case,
+// process_aviris.py:183-219).  The group's spectra are read from HBM exactly ONCE into shared memory
+// (band-major, 73 x 512 floats = 150 KB), and the 30 reweighting iterations never refactorise:
+//   S_it = C0 + t w^T + w t^T + beta t t^T      (t = previous target, w = ma*xbar - X^T a / N,
+//                                                beta = a.a/N - ma^2, ma = mean(a), a = R*mf)
+// is a symmetric rank-two update of the group's plain covariance C0, so with P0 = C0^-1 (one in-place
+// Gauss-Jordan inversion, fp64) the Woodbury identity gives
+//   S_it^-1 b = P0 b - [P0 t, P0 w] (K^-1 + U^T P0 U)^-1 U^T P0 b,   U = [t, w], K^-1 = [[0,1],[1,-beta]],
+// i.e. two 73 x 73 mat-vecs and a 2 x 2 solve per iteration (P0 t is last iteration's P0 b) instead of
+// a covariance rebuild + Cholesky.  Same mathematics as the reference's loop (mag1c.py:233-268), all
+// S x S algebra in fp64.  Per iteration the kernel then makes two passes over the RESIDENT spectra: the
+// matched-filter apply (one thread per pixel) and v = X^T a (one warp per band).
+// ------------------------------------------------------------------------------------------------
+constexpr int kResThreads = 512;
+constexpr int kResMaxP = 512;
+constexpr int kResLdx = 513;       // odd row pitch: band-major rows start on different banks
+
+__device__ __forceinline__ double warp_sum_all(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__host__ __device__ inline int res_sp(int S) { return (S + 7) / 8 * 8; }
+__host__ __device__ inline int res_lda(int S) { return S | 1; }
+__host__ __device__ inline size_t res_smem_bytes(int S) {
+  const int SP = res_sp(S);
+  return (size_t)(S * res_lda(S) + 14 * SP + kResMaxP + 64) * 8 + (size_t)SP * kResLdx * 4 + kResMaxP * 4 + 16;
+}
+
+__global__ void __launch_bounds__(kResThreads, 1)
+mag1c_resident_kernel(const float* __restrict__ x, int64_t pixel_stride, const int32_t* __restrict__ pix_idx,
+                      const int32_t* __restrict__ counts, int pmax, const double* __restrict__ tmpl,
+                      float* __restrict__ mf_out, float* __restrict__ al_out, int S, int num_iter,
+                      int* __restrict__ status) {
+  extern __shared__ double smd[];
+  const int g = blockIdx.x;
+  const int P = counts ? counts[g] : pmax;
+  if (P <= 10) return;                                 // mag1c.py:166-168: too few pixels, outputs stay NODATA
+  const int32_t* idx = pix_idx + (int64_t)g * pmax;
+  const int SP = res_sp(S), LDA = res_lda(S);
+  double* A = smd;                       // S x LDA: C0, then P0 = C0^-1
+  double* xbar = A + S * LDA;
+  double* tp = xbar + SP;                // template
+  double* tprev = tp + SP;               // t: target inside modx
+  double* tcur = tprev + SP;             // b: target = template * mu
+  double* mu = tcur + SP;
+  double* wv = mu + SP;
+  double* pt = wv + SP;                  // P0 t
+  double* pw = pt + SP;                  // P0 w
+  double* pb = pw + SP;                  // P0 b
+  double* cit = pb + SP;
+  double* v = cit + SP;                  // X^T a
+  double* rowk = v + SP;                 // Gauss-Jordan pivot row / column
+  double* colk = rowk + SP;
+  double* spare = colk + SP;
+  double* a_s = spare + SP;              // [512] a = R*mf per pixel
+  double* scal = a_s + kResMaxP;         // [64] scalars + block-reduction scratch
+  float* Xt = reinterpret_cast<float*>(scal + 64);     // [SP][513] band-major spectra
+  int32_t* pidx = reinterpret_cast<int32_t*>(Xt + (size_t)SP * kResLdx);
+  __shared__ int ok;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = kResThreads / 32;
+  const double N = (double)P;
+
+  if (tid == 0) ok = 1;
+  for (int i = tid; i < P; i += kResThreads) pidx[i] = idx[i];
+  for (int i = tid; i < S; i += kResThreads) tp[i] = tmpl[i];
+  for (int i = tid; i < (SP - S) * kResLdx; i += kResThreads) Xt[(size_t)S * kResLdx + i] = 0.f;   // pad bands
+  __syncthreads();
+
+  // ---- the ONE pass over HBM: pixel-major global -> band-major shared.  One warp per pixel, lanes over bands:
+  // coalesced 4*S-byte reads, transposed stores hit consecutive banks (odd row pitch); all loads independent.
+  for (int p0 = warp; p0 < P; p0 += 4 * NW) {
+    float r[4][3];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = p0 + q * NW;
+      const float* xp = x + (int64_t)pidx[p < P ? p : p0] * pixel_stride;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) r[q][k] = (p < P && lane + 32 * k < S) ? xp[lane + 32 * k] : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int p = p0 + q * NW;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (p < P && lane + 32 * k < S) Xt[(size_t)(lane + 32 * k) * kResLdx + p] = r[q][k];
+    }
+  }
+  __syncthreads();
+
+  // ---- xbar: one warp per band ------------------------------------------------------------------------------
+  for (int s2 = warp; s2 < S; s2 += NW) {
+    const float* row = Xt + (size_t)s2 * kResLdx;
+    double acc = 0.0;
+    for (int p = lane; p < P; p += 32) acc += (double)(row[p]);
+    acc = warp_sum_all(acc);
+    if (lane == 0) xbar[s2] = acc / N;
+  }
+  __syncthreads();
+
+  // ---- C0 = X^T X / N - xbar xbar^T: one warp per 8 x 4 tile of the lower triangle, lanes over pixels --------
+  {
+    int t = 0;
+    for (int rb = 0; rb < SP / 8; ++rb) {
+      const int ncb = min(2 * rb + 2, SP / 4);
+      for (int cb = 0; cb < ncb; ++cb, ++t) {
+        if (t % NW != warp) continue;
+        double acc[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) acc[e] = 0.0;
+        const float* ri = Xt + (size_t)(8 * rb) * kResLdx;
+        const float* rj = Xt + (size_t)(4 * cb) * kResLdx;
+        for (int p = lane; p < P; p += 32) {
+          double xi[8], xj[4];
+#pragma unroll
+          for (int a = 0; a < 8; ++a) xi[a] = (double)(ri[(size_t)a * kResLdx + p]);
+#pragma unroll
+          for (int b = 0; b < 4; ++b) xj[b] = (double)(rj[(size_t)b * kResLdx + p]);
+#pragma unroll
+          for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a * 4 + b] = fma(xi[a], xj[b], acc[a * 4 + b]);
+        }
+        // 32 lanes x 32 partial sums -> lane e holds the total of entry e (recursive halving, 31 shuffles)
+#pragma unroll
+        for (int wdt = 16, mask = 16; wdt >= 1; wdt >>= 1, mask >>= 1) {
+          const bool upper = (lane & mask) != 0;
+#pragma unroll
+          for (int e = 0; e < wdt; ++e) {
+            const double send = upper ? acc[e] : acc[e + wdt];
+            const double keep = upper ? acc[e + wdt] : acc[e];
+            acc[e] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+          }
+        }
+        const int i = 8 * rb + (lane >> 2), j = 4 * cb + (lane & 3);
+        if (i < S && j <= i) {
+          const double c = acc[0] / N - xbar[i] * xbar[j];
+          A[i * LDA + j] = c;
+          A[j * LDA + i] = c;
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- P0 = C0^-1 by the symmetric sweep operator (Goodnight): sweeping every pivot of an SPD matrix leaves
+  // -C0^-1.  Each thread keeps its <= 7 lower-triangle entries in REGISTERS for all S sweeps; per sweep only
+  // the pivot row/column is published to shared memory (double buffered: one barrier per sweep).  A
+  // non-positive pivot means C0 is not positive definite (the reference's Cholesky raises).
+  {
+    constexpr int kOwn = 7;                      // ceil(80*81/2 / 512)
+    const int NT = S * (S + 1) / 2;
+    double av[kOwn];
+    int ei[kOwn], ej[kOwn];
+#pragma unroll
+    for (int m = 0; m < kOwn; ++m) {
+      const int e = tid + kResThreads * m;
+      int i = (int)((sqrtf(8.f * (float)e + 1.f) - 1.f) * 0.5f);
+      while (i * (i + 1) / 2 > e) --i;
+      while ((i + 1) * (i + 2) / 2 <= e) ++i;
+      const int j = e - i * (i + 1) / 2;
+      const bool valid = e < NT;
+      ei[m] = valid ? i : -1;
+      ej[m] = valid ? j : -1;
+      av[m] = valid ? A[i * LDA + j] : 0.0;
+    }
+    for (int k = 0; k < S; ++k) {
+      double* ck = (k & 1) ? colk : rowk;
+#pragma unroll
+      for (int m = 0; m < kOwn; ++m) {
+        if (ej[m] == k) ck[ei[m]] = av[m];          // column k below (and on) the diagonal
+        else if (ei[m] == k) ck[ej[m]] = av[m];     // row k left of the diagonal = column k above it
+      }
+      __syncthreads();
+      double d = ck[k];
+      if (!(d > 0.0)) {
+        if (tid == 0) ok = 0;
+        d = 1.0;
+      }
+      const double inv = 1.0 / d;
+#pragma unroll
+      for (int m = 0; m < kOwn; ++m) {
+        const int i = ei[m], j = ej[m];
+        if (i < 0) continue;
+        if (i == k) av[m] = (j == k) ? -inv : ck[j] * inv;
+        else if (j == k) av[m] = ck[i] * inv;
+        else av[m] = fma(-ck[i] * inv, ck[j], av[m]);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < kOwn; ++m) {
+      if (ei[m] < 0) continue;
+      A[ei[m] * LDA + ej[m]] = -av[m];
+      A[ej[m] * LDA + ei[m]] = -av[m];
+    }
+  }
+  __syncthreads();
+
+  // ---- iterations ----------------------------------------------------------------------------------------------
+  double sum_a = 0.0, sum_a2 = 0.0;       // block-uniform
+  float R_f = 0.f, mf_f = 0.f;            // this thread's pixel, working values in the storage precision
+  const int64_t my_pix = tid < P ? (int64_t)pidx[tid] : 0;
+  for (int it = 0; it <= num_iter; ++it) {
+    if (tid < S) {
+      if (it == 0) {
+        mu[tid] = xbar[tid];
+        tcur[tid] = tp[tid] * xbar[tid];          // target0 = template * mean(x)   (mag1c.py:312, :233)
+      } else {
+        const double ma = sum_a / N;
+        const double told = tcur[tid];
+        tprev[tid] = told;
+        pt[tid] = pb[tid];                          // P0 t: last iteration's P0 b
+        const double m = xbar[tid] - ma * told;     // mean of modx = x - a t^T
+        mu[tid] = m;
+        wv[tid] = ma * xbar[tid] - v[tid] / N;
+        tcur[tid] = tp[tid] * m;
+      }
+    }
+    __syncthreads();
+    // pb = P0 b (and pw = P0 w): four threads per matrix row
+    {
+      const int r = tid >> 2, sub = tid & 3;
+      double sb = 0.0, sw = 0.0;
+      if (r < S) {
+        const double* Ar = A + r * LDA;
+        for (int c = sub; c < S; c += 4) {
+          const double aval = Ar[c];
+          sb = fma(aval, tcur[c], sb);
+          if (it > 0) sw = fma(aval, wv[c], sw);
+        }
+      }
+      sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+      sb += __shfl_xor_sync(0xffffffffu, sb, 2);
+      sw += __shfl_xor_sync(0xffffffffu, sw, 1);
+      sw += __shfl_xor_sync(0xffffffffu, sw, 2);
+      if (r < S && sub == 0) {
+        pb[r] = sb;
+        pw[r] = sw;
+      }
+    }
+    __syncthreads();
+    // warp 0: Woodbury 2 x 2 system, cit = S_it^-1 b, and the filter's scalars
+    if (warp == 0) {
+      double g11 = 0.0, g12 = 0.0, g22 = 0.0, r1 = 0.0, r2 = 0.0;
+      if (it > 0) {
+        for (int s2 = lane; s2 < S; s2 += 32) {
+          g11 = fma(tprev[s2], pt[s2], g11);
+          g12 = fma(tprev[s2], pw[s2], g12);
+          g22 = fma(wv[s2], pw[s2], g22);
+          r1 = fma(tprev[s2], pb[s2], r1);
+          r2 = fma(wv[s2], pb[s2], r2);
+        }
+        g11 = warp_sum_all(g11); g12 = warp_sum_all(g12); g22 = warp_sum_all(g22);
+        r1 = warp_sum_all(r1); r2 = warp_sum_all(r2);
+      }
+      double y1 = 0.0, y2 = 0.0;
+      if (it > 0) {
+        const double beta = sum_a2 / N - (sum_a / N) * (sum_a / N);
+        const double m11 = g11, m12 = 1.0 + g12, m22 = g22 - beta;
+        const double det = m11 * m22 - m12 * m12;
+        y1 = (r1 * m22 - m12 * r2) / det;
+        y2 = (m11 * r2 - m12 * r1) / det;
+      }
+      double nrm = 0.0, mucit = 0.0, mumu = 0.0;
+      for (int s2 = lane; s2 < S; s2 += 32) {
+        const double c = it > 0 ? pb[s2] - y1 * pt[s2] - y2 * pw[s2] : pb[s2];
+        cit[s2] = c;
+        nrm = fma(tcur[s2], c, nrm);
+        mucit = fma(mu[s2], c, mucit);
+        mumu = fma(xbar[s2], xbar[s2], mumu);
+      }
+      nrm = warp_sum_all(nrm); mucit = warp_sum_all(mucit); mumu = warp_sum_all(mumu);
+      if (it > 0 && nrm < 1.0) nrm = 1.0;               // mag1c.py:264-266 (not applied inside rmf)
+      if (lane == 0) {
+        scal[0] = nrm;
+        scal[1] = mucit;
+        scal[2] = mumu;
+      }
+    }
+    __syncthreads();
+    // ---- matched-filter apply: one thread per pixel over the resident spectra ------------------------------------
+    const bool last = it == num_iter;
+    const double nrm = scal[0], mucit = scal[1], mumu = scal[2];
+    double la = 0.0, la2 = 0.0;
+    if (tid < P) {
+      const float* xp = Xt + tid;
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+      int s2 = 0;
+      for (; s2 + 4 <= S; s2 += 4) {
+        d0 = fma((double)(xp[(size_t)s2 * kResLdx]), cit[s2], d0);
+        d1 = fma((double)(xp[(size_t)(s2 + 1) * kResLdx]), cit[s2 + 1], d1);
+        d2 = fma((double)(xp[(size_t)(s2 + 2) * kResLdx]), cit[s2 + 2], d2);
+        d3 = fma((double)(xp[(size_t)(s2 + 3) * kResLdx]), cit[s2 + 3], d3);
+      }
+      for (; s2 < S; ++s2) d0 = fma((double)(xp[(size_t)s2 * kResLdx]), cit[s2], d0);
+      const double dot = (d0 + d1) + (d2 + d3);
+      double R, mf;
+      if (it == 0) {
+        double x0 = 0.0, x1 = 0.0;
+        for (s2 = 0; s2 + 2 <= S; s2 += 2) {
+          x0 = fma((double)(xp[(size_t)s2 * kResLdx]), xbar[s2], x0);
+          x1 = fma((double)(xp[(size_t)(s2 + 1) * kResLdx]), xbar[s2 + 1], x1);
+        }
+        for (; s2 < S; ++s2) x0 = fma((double)(xp[(size_t)s2 * kResLdx]), xbar[s2], x0);
+        R = (x0 + x1) / mumu;                            // mag1c.py:330
+        mf = (dot - mucit) / (R * nrm);                  // mag1c.py:332
+        R_f = (float)R;
+        al_out[my_pix] = R_f;
+      } else {
+        R = (double)R_f;
+        const double reg = 1.0 / (R * ((double)mf_f + kEpsilon));   // mag1c.py:255
+        mf = ((dot - mucit) - reg) / (R * nrm);          // mag1c.py:267
+      }
+      mf = mf > 0.0 ? mf : 0.0;                          // relu
+      mf_f = (float)mf;
+      if (last) mf_out[my_pix] = (float)((double)mf_f * kScaling);
+      const double a = (double)R_f * (double)mf_f;
+      a_s[tid] = a;
+      la = a;
+      la2 = a * a;
+    }
+    if (last) break;
+    // block sums of a and a^2
+    la = warp_sum_all(la);
+    la2 = warp_sum_all(la2);
+    if (lane == 0) {
+      scal[8 + warp] = la;
+      scal[8 + NW + warp] = la2;
+    }
+    __syncthreads();                         // also publishes a_s
+    sum_a = 0.0;
+    sum_a2 = 0.0;
+#pragma unroll
+    for (int wq = 0; wq < NW; ++wq) {
+      sum_a += scal[8 + wq];
+      sum_a2 += scal[8 + NW + wq];
+    }
+    // v = X^T a: one warp per band
+    for (int s2 = warp; s2 < S; s2 += NW) {
+      const float* row = Xt + (size_t)s2 * kResLdx;
+      double acc = 0.0;
+      for (int p = lane; p < P; p += 32) acc = fma((double)(row[p]), a_s[p], acc);
+      acc = warp_sum_all(acc);
+      if (lane == 0) v[s2] = acc;
+    }
+    __syncthreads();
+  }
+  if (tid == 0 && !ok && status) atomicAdd(status, 1);
+}
+
 }  // namespace
 
 extern "C" int64_t sc_mag1c_smem_bytes(int S, int pmax, int elem_bytes) {
@@ -331,10 +688,19 @@ extern "C" int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_
                                int num_iter, double alpha, int fp64, int* status, void* stream) {
   if (!x || !pix_idx || !tmpl || !mf_out || !albedo_out || G <= 0 || S < 2 || S + 1 > kThreads || pmax < 1 || num_iter < 0)
     return SC_ERR_BAD_ARG;
-  size_t smem = (size_t)sc_mag1c_smem_bytes(S, pmax, fp64 ? 8 : 4);
-  if (smem > 220 * 1024) return SC_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
+  // group-resident fast path: fp32 radiance, no diagonal loading, <= 512 pixels per group (the AVIRIS case)
+  if (!fp64 && alpha == 0.0 && pmax <= kResMaxP && res_smem_bytes(S) <= 227 * 1024 && !getenv("STARCOP_MAG1C_STREAMING")) {
+    const size_t rs = res_smem_bytes(S);
+    e = cudaFuncSetAttribute(mag1c_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
+    if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
+    mag1c_resident_kernel<<<G, kResThreads, rs, st>>>((const float*)x, pixel_stride, pix_idx, counts, pmax, tmpl,
+                                                      (float*)mf_out, (float*)albedo_out, S, num_iter, status);
+    return check_launch();
+  }
+  size_t smem = (size_t)sc_mag1c_smem_bytes(S, pmax, fp64 ? 8 : 4);
+  if (smem > 220 * 1024) return SC_ERR_UNSUPPORTED;
   if (fp64) {
     e = cudaFuncSetAttribute(mag1c_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
