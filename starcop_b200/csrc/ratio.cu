@@ -5,9 +5,13 @@
 // Kernel 1 (one CTA per tile x band): exact order statistics by a 4-pass radix select on the
 // monotone integer image of the floats (four ranks at once: k, k+1 for each percentile), then the
 // inlier sum.  Kernel 2: the coalesced, vectorised elementwise product.
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 using namespace sc;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -112,6 +116,237 @@ __global__ void ratio_apply_kernel(const float* __restrict__ bg, const float* __
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Cluster-resident variant (tiles of <= 512 x 512 pixels): ONE thread-block cluster of 8 CTAs per tile.
+// Each CTA keeps its eighth of the current band in shared memory (<= 128 KB), so every band is read from
+// HBM once; the radix-select histograms of the 8 CTAs are merged through distributed shared memory
+// (each CTA sums all eight histograms itself: no broadcast step, one cluster barrier per pass thanks to
+// ping-pong histogram buffers).  Keys are made relative to the band's minimum and only the
+// ceil(bits(max-min)/8) significant digits are scanned (3 passes for typical radiances instead of 4, and
+// a well-spread first histogram instead of everything landing in one exponent bucket).  The ratio is
+// applied straight from the resident signal band.  HBM traffic = bg + sig read once (+ bg re-read from
+// L2) + the output = the product's algorithmic 12 B / pixel.
+// ------------------------------------------------------------------------------------------------
+constexpr int kClu = 8;
+constexpr int kCluThreads = 1024;
+constexpr int kCluMaxSlice = 32768;      // floats per CTA: 128 KB
+
+__device__ __forceinline__ double block_sum_1024(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0.0;
+  for (int i = 0; i < kCluThreads / 32; ++i) t += red[i];      // fixed order: deterministic
+  return t;
+}
+
+__global__ void __cluster_dims__(kClu, 1, 1) __launch_bounds__(kCluThreads, 1)
+ratio_cluster_kernel(const float* __restrict__ bg, const float* __restrict__ sig, float* __restrict__ out, int64_t HW,
+                     SelectRanks sr, float zero_value, double* __restrict__ ws) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int tile = blockIdx.x / kClu;
+  extern __shared__ __align__(16) float data[];              // this CTA's slice of the current band
+  __shared__ unsigned int hist[2][4][256];                   // ping-pong, read remotely by the whole cluster
+  __shared__ unsigned int tot[4][256];
+  __shared__ uint32_t s_mm[2];                               // local min / max key, read remotely
+  __shared__ double s_part;                                  // local inlier sum, read remotely
+  __shared__ uint32_t s_g[2];                                // cluster-wide min / max key
+  __shared__ uint32_t prefix[4];
+  __shared__ long long rank[4];
+  __shared__ double red[kCluThreads / 32];
+  __shared__ uint32_t wred[2][kCluThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = (int)((((HW + kClu - 1) / kClu) + 3) & ~(int64_t)3);
+  const int64_t start = (int64_t)crank * slice;
+  const int n = (int)(HW - start < 0 ? 0 : (HW - start < slice ? HW - start : slice));
+  double band_sum[2] = {0.0, 0.0}, band_lo[2] = {0.0, 0.0}, band_hi[2] = {0.0, 0.0};
+  int pp = 0;                                                // ping-pong index, advances once per pass
+
+  for (int band = 0; band < 2; ++band) {
+    const float* src = (band == 0 ? bg : sig) + (int64_t)tile * HW + start;
+    // ---- load the slice, local min / max key ---------------------------------------------------------
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    if ((HW & 3) == 0) {
+      const float4* s4 = reinterpret_cast<const float4*>(src);
+      float4* d4 = reinterpret_cast<float4*>(data);
+      for (int i = tid; i < n / 4; i += kCluThreads) {
+        const float4 v = s4[i];
+        d4[i] = v;
+        const uint32_t k0 = f2key(v.x), k1 = f2key(v.y), k2 = f2key(v.z), k3 = f2key(v.w);
+        kmin = min(min(kmin, k0), min(min(k1, k2), k3));
+        kmax = max(max(kmax, k0), max(max(k1, k2), k3));
+      }
+    } else {
+      for (int i = tid; i < n; i += kCluThreads) {
+        const float v = src[i];
+        data[i] = v;
+        const uint32_t k = f2key(v);
+        kmin = min(kmin, k);
+        kmax = max(kmax, k);
+      }
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) {
+      wred[0][warp] = kmin;
+      wred[1][warp] = kmax;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      kmin = __reduce_min_sync(0xffffffffu, wred[0][lane]);
+      kmax = __reduce_max_sync(0xffffffffu, wred[1][lane]);
+      if (lane == 0) {
+        s_mm[0] = kmin;
+        s_mm[1] = kmax;
+      }
+    }
+    cluster.sync();
+    if (warp == 0) {
+      uint32_t a = 0xffffffffu, b = 0u;
+      if (lane < kClu) {
+        const uint32_t* r = cluster.map_shared_rank(s_mm, lane);
+        a = r[0];
+        b = r[1];
+      }
+      a = __reduce_min_sync(0xffffffffu, a);
+      b = __reduce_max_sync(0xffffffffu, b);
+      if (lane == 0) {
+        s_g[0] = a;
+        s_g[1] = b;
+      }
+      if (lane < 4) {
+        prefix[lane] = 0;
+        rank[lane] = sr.r[lane];
+      }
+    }
+    __syncthreads();
+    const uint32_t gmin = s_g[0];
+    const uint32_t range = s_g[1] - gmin;
+    const int nb = range ? 32 - __clz(range) : 1;
+    const int npass = (nb + 7) / 8, nbp = 8 * npass;
+    // ---- radix select of the four ranks over the significant digits ---------------------------------------
+    for (int pass = 0; pass < npass; ++pass, pp ^= 1) {
+      const int shift = nbp - 8 * (pass + 1);
+      unsigned int (*h)[256] = hist[pp];
+      for (int i = tid; i < 4 * 256; i += kCluThreads) (&h[0][0])[i] = 0;
+      // ranks whose prefix equals an earlier rank's share that rank's histogram
+      uint32_t pf[4];
+      int uq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        pf[q] = prefix[q];
+        uq[q] = q;
+        for (int q2 = q - 1; q2 >= 0; --q2)
+          if (pf[q2] == pf[q]) uq[q] = q2;
+      }
+      __syncthreads();
+      const int n_pad = (n + 31) & ~31;
+      for (int i = tid; i < n_pad; i += kCluThreads) {
+        const bool valid = i < n;
+        const uint32_t rk = valid ? f2key(data[i]) - gmin : 0u;
+        const uint32_t b = (rk >> shift) & 255u;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (uq[q] != q) continue;                                   // block-uniform
+          const bool hit = valid && (pass == 0 || (rk >> (shift + 8)) == (pf[q] >> (shift + 8)));
+          // the relative keys spread the first digit over all 256 buckets, so plain shared atomics are
+          // conflict-light; a warp whose 32 elements all fall in ONE bucket (constant / nodata regions)
+          // adds once (MATCH.ALL is a single compare; MATCH.ANY was measured ~10x slower here)
+          int all_same;
+          __match_all_sync(0xffffffffu, hit ? b : 0xffffffffu, &all_same);
+          if (all_same) {
+            if (hit && lane == 0) atomicAdd(&h[q][b], 32u);
+          } else if (hit) {
+            atomicAdd(&h[q][b], 1u);
+          }
+        }
+      }
+      __syncthreads();
+      cluster.sync();
+      {
+        const int q = tid >> 8, b = tid & 255;
+        unsigned int t = 0;
+        if (uq[q] == q) {
+#pragma unroll
+          for (int r = 0; r < kClu; ++r) t += cluster.map_shared_rank(&hist[pp][q][b], r)[0];
+        }
+        tot[q][b] = t;
+      }
+      __syncthreads();
+      if (warp < 4) {
+        // warp q finds the bucket holding rank[q]: 8 bins per lane, warp scan of the lane totals
+        const int q = warp;
+        const unsigned int* tq = tot[uq[q]];
+        unsigned int c8[8], ls = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          c8[k] = tq[lane * 8 + k];
+          ls += c8[k];
+        }
+        unsigned int incl = ls;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const long long r = rank[q];
+        const long long excl = (long long)incl - ls;
+        const bool mine = r >= excl && r < (long long)incl;
+        if (mine) {
+          long long rr = r - excl;
+          int k = 0;
+          for (; k < 7; ++k) {
+            if (rr < (long long)c8[k]) break;
+            rr -= c8[k];
+          }
+          rank[q] = rr;
+          prefix[q] = pf[q] | ((uint32_t)(lane * 8 + k) << shift);
+        }
+      }
+      __syncthreads();
+    }
+    // ---- percentile bounds (np.percentile linear interpolation) and the inlier sum -----------------------------
+    const double a0 = key2f(prefix[0] + gmin), a1 = key2f(prefix[1] + gmin);
+    const double b0 = key2f(prefix[2] + gmin), b1 = key2f(prefix[3] + gmin);
+    const double lo = np_lerp(a0, a1, sr.t_lo), hi = np_lerp(b0, b1, sr.t_hi);
+    double sacc = 0.0;
+    for (int i = tid; i < n; i += kCluThreads) {
+      const double v = (double)data[i];
+      if (v >= lo && v <= hi) sacc += v;
+    }
+    sacc = block_sum_1024(sacc, red);
+    if (tid == 0) s_part = sacc;
+    cluster.sync();
+    double total = 0.0;
+    for (int r = 0; r < kClu; ++r) total += *cluster.map_shared_rank(&s_part, r);    // fixed order: deterministic
+    band_sum[band] = total;
+    band_lo[band] = lo;
+    band_hi[band] = hi;
+    cluster.sync();            // everyone has read s_part / the last histograms before they are reused
+  }
+  if (crank == 0 && tid == 0 && ws) {
+    for (int band = 0; band < 2; ++band) {
+      double* o = ws + ((int64_t)tile * 2 + band) * 3;
+      o[0] = band_sum[band];
+      o[1] = band_lo[band];
+      o[2] = band_hi[band];
+    }
+  }
+  // ---- apply: the signal band is resident, the background band is re-read (L2) -------------------------------
+  const float c = (float)band_sum[0] / (float)band_sum[1];     // numpy: float32 scalar
+  const float* bgp = bg + (int64_t)tile * HW + start;
+  float* op = out + (int64_t)tile * HW + start;
+  for (int i = tid; i < n; i += kCluThreads) {
+    const float b = bgp[i], sv = data[i];
+    float r = (c * sv - b) / (b + 1e-6f);
+    if (sv < 1e-6f && b < 1e-6f) r = zero_value;
+    op[i] = r;
+  }
+}
+
 }  // namespace
 
 extern "C" int64_t sc_ratio_workspace_bytes(int T, int64_t HW) {
@@ -134,6 +369,21 @@ extern "C" int sc_ratio_product(const float* bg, const float* sig, float* out, i
   sr.r[2] = khi;
   sr.r[3] = khi + 1 < HW ? khi + 1 : HW - 1;
   cudaStream_t st = (cudaStream_t)stream;
+  // measured on B200 (scripts/ratio_bench.py): one cluster per tile wins while the tiles do not fill the GPU
+  // (T = 8: 99 us vs 259 us); from ~64 tiles on, two independent CTAs per tile keep more SMs busy
+  if (HW <= (int64_t)kClu * kCluMaxSlice && (T < 64 || getenv("STARCOP_RATIO_CLUSTER")) && !getenv("STARCOP_RATIO_NOCLUSTER")) {
+    const int slice = (int)((((HW + kClu - 1) / kClu) + 3) & ~(int64_t)3);
+    const size_t smem = (size_t)slice * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(ratio_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kCluMaxSlice * (int)sizeof(float));
+      if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
+      attr_set = true;
+    }
+    ratio_cluster_kernel<<<T * kClu, kCluThreads, smem, st>>>(bg, sig, out, HW, sr, zero_value, (double*)workspace);
+    return check_launch();
+  }
   ratio_select_kernel<<<dim3(2, T), kSelThreads, 0, st>>>(bg, sig, HW, sr, (double*)workspace);
   int64_t total = (int64_t)T * HW;
   int blocks = (int)((total + 255) / 256);
