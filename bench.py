@@ -318,7 +318,14 @@ def main():
         }
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # The captured CUDA graphs hold NCCL work: destroying the communicator (or normal interpreter teardown)
+        # with them alive was observed to hang forever AFTER the result line was printed.  Quiesce, agree that
+        # every rank is done, flush, and leave without running the NCCL / graph destructors.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
