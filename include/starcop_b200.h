@@ -202,6 +202,16 @@ int sc_tc_cin_pad(int Cin);
 int sc_tc_supported(void);
 int sc_tc_pack_weights(const float* w_oihw, void* w_bf16, int Cout, int Cin, int KH, int KW,
                        int flip_transpose, int cin_pad, int cout_pad, void* stream);
+/* the same re-pack for MANY layers in one launch (the weights change once per optimiser step: the engine
+ * re-packs every tensor-core layer's fprop and dgrad filters at the start of a step).  descs_dev: device array
+ * of n <= 128 jobs; offset = running sum of the jobs' output element counts (rows * kk * cols), total = their sum. */
+typedef struct {
+  const float* w;          /* OIHW f32 */
+  void* out;               /* bf16 [rows][kk][cols] */
+  int64_t offset;
+  int32_t cout, cin, kk, flip_transpose, cin_pad, cout_pad;
+} sc_tc_pack_desc;
+int sc_tc_pack_weights_batch(const sc_tc_pack_desc* descs_dev, int n, int64_t total, void* stream);
 int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void* y, int ldy, double* stats,
                      int* stats_rows_host, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                      int stride, int accumulate, void* stream);

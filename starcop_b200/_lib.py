@@ -50,6 +50,7 @@ SIGNATURES = {
     "sc_threshold_opening": [P, F, P, P, I, I, I, P],
     "sc_tc_supported": [],
     "sc_tc_pack_weights": [P, P, I, I, I, I, I, I, I, P],
+    "sc_tc_pack_weights_batch": [P, I, L, P],
     "sc_tc_cin_pad": [I],
     "sc_tc_conv_fprop": [P, I, P, P, I, P, P, I, I, I, I, I, I, I, I, I, P],
     "sc_tc_halo_cin_pad": [I],

@@ -114,6 +114,44 @@ extern "C" int sc_tc_pack_weights(const float* w_oihw, void* w_bf16, int Cout, i
   return check_launch();
 }
 
+// All of a step's weight re-packs in ONE launch: `descs` is a device table of n jobs (see sc_tc_pack_desc in the
+// header), job j covering output elements [offset_j, offset_{j+1}) of the concatenated index space.
+__global__ void tc_pack_weights_batch_kernel(const sc_tc_pack_desc* __restrict__ descs, int n, int64_t total) {
+  __shared__ int64_t s_off[129];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_off[i] = descs[i].offset;
+  if (threadIdx.x == 0) s_off[n] = total;
+  __syncthreads();
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {                       // last job whose offset <= g
+      const int mid = (lo + hi + 1) >> 1;
+      if (s_off[mid] <= g) lo = mid; else hi = mid - 1;
+    }
+    const sc_tc_pack_desc d = descs[lo];
+    const int64_t i = g - d.offset;
+    const int cols = d.flip_transpose ? d.cout_pad : d.cin_pad;
+    const int c = (int)(i % cols);
+    const int64_t t = i / cols;
+    const int tap = (int)(t % d.kk);
+    const int r = (int)(t / d.kk);
+    float v = 0.f;
+    if (!d.flip_transpose) {
+      if (r < d.cout && c < d.cin) v = d.w[((int64_t)r * d.cin + c) * d.kk + tap];
+    } else {
+      if (r < d.cin && c < d.cout) v = d.w[((int64_t)c * d.cin + r) * d.kk + (d.kk - 1 - tap)];
+    }
+    reinterpret_cast<__nv_bfloat16*>(d.out)[i] = __float2bfloat16_rn(v);
+  }
+}
+
+extern "C" int sc_tc_pack_weights_batch(const sc_tc_pack_desc* descs_dev, int n, int64_t total, void* stream) {
+  if (!descs_dev || n < 1 || n > 128 || total < 1) return SC_ERR_BAD_ARG;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  tc_pack_weights_batch_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, n, total);
+  return check_launch();
+}
+
 // ------------------------------------------------------------------------------------------------
 // fprop
 // ------------------------------------------------------------------------------------------------

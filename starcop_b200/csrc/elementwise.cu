@@ -102,15 +102,23 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __rest
       s[i] = q[i] = 0.0;
       fs[i] = fq[i] = 0.f;
     }
+    // 4 pixels per trip: all four 16-byte loads are issued before any arithmetic (the grid is capped at
+    // 296 CTAs by the partial-row protocol, so per-thread memory parallelism is what fills the HBM pipe)
     int run = 0;
-    for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
-      f8 v = load8<T>(y + p * ldy + cv * 8);
+    const int64_t stride = (int64_t)gridDim.x * PL;
+    int64_t p = (int64_t)blockIdx.x * PL + pl;
+    for (; p + 3 * stride < P; p += 4 * stride) {
+      f8 v4[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        fs[i] += v.v[i];
-        fq[i] = fmaf(v.v[i], v.v[i], fq[i]);
-      }
-      if (++run == 16) {
+      for (int u = 0; u < 4; ++u) v4[u] = load8<T>(y + (p + u * stride) * ldy + cv * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          fs[i] += v4[u].v[i];
+          fq[i] = fmaf(v4[u].v[i], v4[u].v[i], fq[i]);
+        }
+      if ((run += 4) >= 16) {
         run = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -118,6 +126,14 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __rest
           q[i] += (double)fq[i];
           fs[i] = fq[i] = 0.f;
         }
+      }
+    }
+    for (; p < P; p += stride) {
+      f8 v = load8<T>(y + p * ldy + cv * 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        fs[i] += v.v[i];
+        fq[i] = fmaf(v.v[i], v.v[i], fq[i]);
       }
     }
     // stage this thread's 16 partials: sm[pl][cvl][16] (no shared-memory atomics: with few channels
@@ -305,7 +321,7 @@ __device__ __forceinline__ f8 load_dz(const T* dz, int lddz, int pooled, int64_t
 }
 
 template <typename T>
-__global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int pooled, const T* __restrict__ y,
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int pooled, const T* __restrict__ y,
                                      int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, int act,
                                      double* __restrict__ partials, int64_t P, int C, int H, int W, int CVB, int PL) {
@@ -326,10 +342,12 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int poo
       s[i] = q[i] = 0.0;
       fs[i] = fq[i] = 0.f;
     }
+    // 2 pixels per trip, loads first (see bn_stats_kernel: the 296-CTA cap makes per-thread memory
+    // parallelism the lever; measured 2.8 TB/s with one pixel per trip)
     int run = 0;
-    for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < P; p += (int64_t)gridDim.x * PL) {
-      f8 yv = load8<T>(y + p * ldy + cv * 8);
-      f8 g = load_dz<T>(dz, lddz, pooled, p, cv, H, W);
+    const int64_t stride = (int64_t)gridDim.x * PL;
+    int64_t p = (int64_t)blockIdx.x * PL + pl;
+    auto accum = [&](const f8& yv, const f8& g) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         float gi = g.v[i] * act_mask(fmaf(yv.v[i], sc_.v[i], sh.v[i]), act);
@@ -337,7 +355,16 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int poo
         fs[i] += gi;
         fq[i] = fmaf(gi, xh, fq[i]);
       }
-      if (++run == 16) {
+    };
+    for (; p + stride < P; p += 2 * stride) {
+      f8 y4[2], g4[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) y4[u] = load8<T>(y + (p + u * stride) * ldy + cv * 8);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) g4[u] = load_dz<T>(dz, lddz, pooled, p + u * stride, cv, H, W);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) accum(y4[u], g4[u]);
+      if ((run += 2) >= 16) {
         run = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -346,6 +373,11 @@ __global__ void bn_bwd_reduce_kernel(const T* __restrict__ dz, int lddz, int poo
           fs[i] = fq[i] = 0.f;
         }
       }
+    }
+    for (; p < P; p += stride) {
+      f8 yv = load8<T>(y + p * ldy + cv * 8);
+      f8 g = load_dz<T>(dz, lddz, pooled, p, cv, H, W);
+      accum(yv, g);
     }
     // stage this thread's 16 partials: sm[pl][cvl][16] (no shared-memory atomics: with few channels
     // hundreds of threads would contend on a handful of fp64 CAS loops)

@@ -97,6 +97,10 @@ class UNetEngine:
         self.stream = 0
         self.use_tc = self.dtype == SC_BF16 and bool(_lib.load().sc_tc_supported())
         self.use_halo = os.environ.get("STARCOP_NO_HALO", "") == ""
+        self._packs = {}                 # (weight name, flip) -> (bf16 buffer, descriptor fields), insertion ordered
+        self._pack_table = None
+        self._packed_this_step = False
+        self._plan_complete = False      # set once a full forward + backward has recorded every request
 
     # ------------------------------------------------------------------ memory
     def begin_step(self):
@@ -198,6 +202,43 @@ class UNetEngine:
         return (self.dtype == SC_BF16 and self.use_tc and (stride == 1 or (stride == 2 and k == 3)) and k in (1, 3)
                 and cout % 8 == 0 and wo % 16 == 0 and ho % 8 == 0 and x.ld % 8 == 0)
 
+    # ------------------------------------------------------------------ packed bf16 weights
+    def _packed(self, wname, k, flip, cpad_in, cpad_out):
+        """Device pointer of the tensor-core packing of weight `wname` (flip=1: the dgrad filter).  The first
+        training step records every request (and packs it on the spot); from then on ALL of them are re-packed
+        by ONE launch at the start of each step (`_pack_all`), and this is a table lookup."""
+        key = (wname, flip)
+        ent = self._packs.get(key)
+        w = self.p[wname]
+        cout, cin = w.shape[0], w.shape[1]
+        if ent is None:
+            rows, cols = (cpad_in, cpad_out) if flip else (cpad_out, cpad_in)
+            buf = torch.empty(rows * k * k * cols, dtype=torch.bfloat16, device=self.device)
+            ent = self._packs[key] = (buf, (w.data_ptr(), buf.data_ptr(), cout, cin, k * k, flip, cpad_in, cpad_out))
+            self._pack_table = None                      # plan changed: rebuild the device table
+        if not self._packed_this_step:
+            call("sc_tc_pack_weights", w.data_ptr(), ent[0].data_ptr(), cout, cin, k, k, flip, cpad_in, cpad_out, self.stream)
+        return ent[0].data_ptr()
+
+    def _pack_all(self):
+        """One launch re-packing every recorded weight (sc_tc_pack_weights_batch); False until a plan exists."""
+        self._packed_this_step = False
+        if not self._packs or not self._plan_complete:
+            return
+        if self._pack_table is None:
+            import numpy as np
+            desc = np.zeros(len(self._packs), dtype=np.dtype([("w", "<u8"), ("out", "<u8"), ("offset", "<i8"), ("cout", "<i4"),
+                                                                ("cin", "<i4"), ("kk", "<i4"), ("flip", "<i4"),
+                                                                ("cin_pad", "<i4"), ("cout_pad", "<i4")]))
+            off = 0
+            for i, (buf, d) in enumerate(self._packs.values()):
+                desc[i] = (d[0], d[1], off, d[2], d[3], d[4], d[5], d[6], d[7])
+                off += buf.numel()
+            self._pack_table = (torch.from_numpy(desc.view(np.uint8).copy()).to(self.device), len(self._packs), off)
+        tab, n, total = self._pack_table
+        call("sc_tc_pack_weights_batch", tab.data_ptr(), n, total, self.stream)
+        self._packed_this_step = True
+
     def _halo_ok(self, x, cin, cout, k, stride):
         """thin 3x3 layers (decoder blocks 2-4): one staged halo patch per tile + resident weights (conv_tc_halo.cu)"""
         # measured on B200 (profiles/r01_layer_bench.txt): it wins where both channel counts are <= 32
@@ -216,16 +257,14 @@ class UNetEngine:
         if self._halo_ok(x, cin, cout, k, stride):
             lib = _lib.load()
             cpad = lib.sc_tc_halo_cin_pad(cin)
-            wb = self.arena.alloc(cout * 9 * cpad * 2)
-            call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, 3, 3, 0, cpad, cout, self.stream)
+            wb = self._packed(wname, 3, 0, cpad, cout)
             part, n = (self._partials(cout), ctypes.c_int(0)) if want_stats else (0, ctypes.c_int(0))
             call("sc_tc_conv3x3_halo", x.ptr, x.ld, wb, y.ptr, y.ld, part, ctypes.byref(n), x.N, x.H, x.W, cin, cout, 0,
                  self.stream)
             return y, ((part, n.value) if want_stats else None)
         if self._tc_ok(x, cin, cout, k, stride):
             cpad = _lib.load().sc_tc_cin_pad(cin)
-            wb = self.arena.alloc(cout * k * k * cpad * 2)
-            call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, k, k, 0, cpad, cout, self.stream)
+            wb = self._packed(wname, k, 0, cpad, cout)
             # the statistics epilogue costs ~(Cout/16) x 300 cycles per 128-pixel tile: worth fusing only
             # when the tile's K loop is long enough to hide it, else the separate pass over y is cheaper
             want_stats = want_stats and cin * k * k >= 256
@@ -256,14 +295,12 @@ class UNetEngine:
             if tc and self._halo_ok(dy, cout, cin, k, 1) and dst.ld % 8 == 0:
                 lib = _lib.load()
                 cpad = lib.sc_tc_halo_cin_pad(cout)
-                wb = self.arena.alloc(cin * 9 * cpad * 2)
-                call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, 3, 3, 1, cin, cpad, self.stream)
+                wb = self._packed(wname, 3, 1, cin, cpad)
                 call("sc_tc_conv3x3_halo", dy.ptr, dy.ld, wb, dst.ptr, dst.ld, 0, 0, dy.N, dy.H, dy.W, cout, cin, acc,
                      self.stream)
             elif tc:
                 cpad = _lib.load().sc_tc_cin_pad(cout)          # dgrad conv: input channels = Cout
-                wb = self.arena.alloc(cin * k * k * cpad * 2)
-                call("sc_tc_pack_weights", w.data_ptr(), wb, cout, cin, k, k, 1, cin, cpad, self.stream)
+                wb = self._packed(wname, k, 1, cin, cpad)
                 call("sc_tc_conv_fprop", dy.ptr, dy.ld, wb, dst.ptr, dst.ld, 0, 0, dy.N, dy.H, dy.W, cout, cin, k, k,
                      1, acc, self.stream)
             else:
@@ -353,6 +390,8 @@ class UNetEngine:
         N, H, W = x_nhwc.N, x_nhwc.H, x_nhwc.W
         assert H % 32 == 0 and W % 32 == 0, "input height and width must be divisible by 32 (smp check_input_shape)"
         self.tape = []
+        if self.use_tc:
+            self._pack_all()
         E = "encoder.features"
         skip_c = (16, 24, 32, 96)                          # f1..f4
         # decoder concat buffers: [upsampled | skip], block i works at stride 16 >> i
@@ -415,3 +454,4 @@ class UNetEngine:
         for fn in reversed(self.tape):
             fn()
         self.tape = []
+        self._plan_complete = True          # every fprop and dgrad packing request of the network is now recorded

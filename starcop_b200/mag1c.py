@@ -3,9 +3,13 @@
 ``get_mask_bad_bands`` (:98-113), plus the tile driver used by ``run_mag1c``
 (starcop/process_aviris.py:183-219: BIP cube, contiguous band slice, groups = detector columns).
 
-Template generation (``generate_template_from_bands``, a one-off host computation over the
-31800-sample CH4 look-up table) stays on the host and is passed in as an array.
+Template generation (``generate_template_from_bands``, :60-95, a one-off computation over the
+31800-sample CH4 look-up table) is host numpy here as in the reference; the filter takes its result
+as an array.
 """
+import os
+import re
+
 import numpy as np
 import torch
 
@@ -14,6 +18,61 @@ from . import _lib
 NODATA = -9999
 SCALING = 1e5
 EPSILON = 1e-9
+
+
+CH4_CONCENTRATIONS = (0, 500, 1000, 2000, 4000, 8000, 16000)      # ppm*m columns of ch4.lut (mag1c.py:79)
+
+
+def read_ch4_lut(lut_dir=None):
+    """The reference ships its radiative-transfer look-up table as an ENVI pair ``ch4.hdr`` / ``ch4.lut``
+    next to ``starcop/models/mag1c.py`` and reads it with ``spectral`` (:75-78).  Same data without that
+    dependency: little-endian float64, BIP with one sample per line -> (7 concentrations, n wavelengths),
+    wavelengths (nm) from the header's ``wavelength = {...}`` list.
+    ``lut_dir`` defaults to $STARCOP_CH4_LUT_DIR, then to an importable ``starcop.models`` package."""
+    if lut_dir is None:
+        lut_dir = os.environ.get("STARCOP_CH4_LUT_DIR")
+    if lut_dir is None:
+        try:
+            import starcop.models as _m          # the reference package, if it is installed
+            lut_dir = os.path.dirname(os.path.abspath(_m.__file__))
+        except Exception as e:                   # noqa: BLE001
+            raise FileNotFoundError("ch4.hdr / ch4.lut not found: pass lut_dir= or set STARCOP_CH4_LUT_DIR") from e
+    with open(os.path.join(lut_dir, "ch4.hdr")) as f:
+        hdr = f.read()
+    m = re.search(r"wavelength\s*=\s*\{([^}]*)\}", hdr)
+    if m is None:
+        raise ValueError("ch4.hdr has no wavelength list")
+    wave = np.array([float(v) for v in m.group(1).replace("\n", " ").split(",") if v.strip()], dtype=np.float64)
+    raw = np.fromfile(os.path.join(lut_dir, "ch4.lut"), dtype="<f8")
+    nconc = len(CH4_CONCENTRATIONS)
+    if raw.size != wave.size * nconc:
+        raise ValueError(f"ch4.lut holds {raw.size} values, expected {wave.size} wavelengths x {nconc} concentrations")
+    return raw.reshape(wave.size, nconc).T.copy(), wave
+
+
+def generate_template_from_bands(centers, fwhm, lut=None, lut_dir=None):
+    """mag1c.py:60-95: the CH4 unit absorption spectrum of a sensor's bands.  Each band is a Gaussian
+    spectral response (sigma = fwhm / 2.355) normalised to unit sum over the LUT's wavelength grid; the
+    LUT radiances are resampled through it, and the per-band slope of log(radiance) against concentration
+    (least squares over the 7 LUT columns) times 1e5 is the template.  Returns (K, 2): [center, spectrum].
+    ``lut`` = (rads (7, n), wave (n,)) overrides the files."""
+    centers = np.asarray(centers)
+    fwhm = np.asarray(fwhm)
+    if np.any(~np.isfinite(centers)) or np.any(~np.isfinite(fwhm)):
+        raise RuntimeError("Band Wavelengths Centers/FWHM data contains non-finite data (NaN or Inf).")
+    if centers.shape[0] != fwhm.shape[0]:
+        raise RuntimeError("Length of band center wavelengths and band fwhm arrays must be equal.")
+    rads, wave = lut if lut is not None else read_ch4_lut(lut_dir)
+    conc = np.asarray(CH4_CONCENTRATIONS)
+    var = (fwhm / (2.0 * np.sqrt(2.0 * np.log(2.0)))) ** 2
+    resp = np.exp(-(wave[:, None] - centers[None, :]) ** 2 / (2 * var)) / (2 * np.pi * var) ** 0.5
+    tot = resp.sum(axis=0)
+    resp = np.divide(resp, tot, where=tot > 0)
+    resampled = np.asarray(rads).dot(resp)
+    lograd = np.log(resampled, where=resampled > 0)
+    design = np.stack((np.ones_like(conc), conc)).T
+    slope, _, _, _ = np.linalg.lstsq(design, lograd, rcond=None)
+    return np.stack((centers, slope[1, :] * SCALING)).T
 
 
 def get_mask_bad_bands(wave):

@@ -226,13 +226,20 @@ def test_graphed_train_step_matches_eager():
 
 
 def test_graphed_step_prefetch_from_pinned_host_matches_direct_stepping():
-    """double-buffered inputs: the H2D copy of batch i+1 overlaps step i; losses equal the plain graphed loop"""
+    """double-buffered inputs: the H2D copy of batch i+1 overlaps step i; every step must see ITS batch.
+    Batch i carries weight_loss scaled by (i+1)^2, so its loss is ~(i+1)^2 x the base loss: a stale or swapped
+    input buffer shows up as a factor, far above the ~0.5 % run-to-run drift of two bf16 training runs
+    (fp32-atomic summation order in the weight gradients, BatchNorm over 8 pixels at this tile size)."""
     torch.manual_seed(7)
     m1 = get_model(default_settings(pos_weight=1.0, compute_dtype="bf16"), None).to(DEV)
     torch.manual_seed(7)
     m2 = get_model(default_settings(pos_weight=1.0, compute_dtype="bf16"), None).to(DEV)
     m1.train(); m2.train()
-    host = [synthetic.hyperstarcop_batch(2, size=64, seed=60 + s) for s in range(4)]
+    host = []
+    for i in range(4):
+        b = synthetic.hyperstarcop_batch(2, size=64, seed=60)           # same tiles: only the weights differ
+        b["weight_loss"] = b["weight_loss"] * float((i + 1) ** 2)
+        host.append(b)
     pinned = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in b.items()} for b in host]
     s1 = m1.make_graphed_train_step(to_dev(host[0]), warmup=1)
     s2 = m2.make_graphed_train_step(to_dev(host[0]), warmup=1, double_buffer=True)
@@ -243,11 +250,9 @@ def test_graphed_step_prefetch_from_pinned_host_matches_direct_stepping():
         if i + 1 < 4:
             s2.prefetch(pinned[i + 1])
         l2.append(s2().item())
-    # both models took one eager warm-up step first: fp32-atomic summation order in the weight gradients lets
-    # the two runs drift by ~1e-4 (see the Adam test), a wrong or stale input buffer would be off by percents
     for i, (a, b) in enumerate(zip(l1, l2)):
-        assert abs(a - b) <= 2e-3 * abs(a), (i, a, b)
-    assert max(l1) - min(l1) > 1e-2 * max(l1)        # the four batches really differ (so buffer mix-ups would show)
+        assert abs(a - b) <= 2e-2 * abs(a), (i, a, b)
+    assert all(l2[i + 1] > 1.5 * l2[i] for i in range(3)), l2      # ((i+2)/(i+1))^2 >= 16/9
     with pytest.raises(AssertionError):
         s2()                                   # nothing prefetched
 

@@ -84,3 +84,46 @@ def test_tiling_matches_oracle_and_notebook_counts():
     assert tiling.has_plume(torch.from_numpy(lab)) == ot.has_plume(lab) == False
     for v in (1242, 1280, 70, 8):
         assert tiling.find_padding(v, 32) == ot.find_padding(v, 32)
+
+
+def test_generate_template_known_answer_on_a_synthetic_lut():
+    """A9 (mag1c.py:60-95) on an analytic look-up table: radiance = exp(-k(lambda) * c) has log-slope -k, so the
+    template of a narrow band is -k(center) * 1e5; also the reference's argument checks."""
+    import numpy as np
+    import pytest
+    from starcop_b200 import mag1c
+    wave = np.linspace(2000.0, 2500.0, 5001)
+    k = 1e-5 * (1.0 + 0.5 * np.sin(wave / 40.0))
+    rads = np.exp(-k[None, :] * np.asarray(mag1c.CH4_CONCENTRATIONS, dtype=np.float64)[:, None])
+    centers = np.array([2100.0, 2250.0, 2400.0])
+    out = mag1c.generate_template_from_bands(centers, np.full(3, 0.5), lut=(rads, wave))
+    assert out.shape == (3, 2) and np.array_equal(out[:, 0], centers)
+    assert np.allclose(out[:, 1], -np.interp(centers, wave, k) * 1e5, rtol=2e-4)
+    # a wide band averages the RADIANCE (not k): compare with the definition evaluated directly
+    wide = mag1c.generate_template_from_bands([2250.0], [30.0], lut=(rads, wave))[0, 1]
+    g = np.exp(-(wave - 2250.0) ** 2 / (2 * (30.0 / 2.3548200450309493) ** 2)); g /= g.sum()
+    slope = np.polyfit(np.asarray(mag1c.CH4_CONCENTRATIONS, float), np.log(rads @ g), 1)[0]
+    assert abs(wide - slope * 1e5) <= 1e-9 * abs(wide)
+    with pytest.raises(RuntimeError):
+        mag1c.generate_template_from_bands([2100.0, np.nan], [5.0, 5.0], lut=(rads, wave))
+    with pytest.raises(RuntimeError):
+        mag1c.generate_template_from_bands([2100.0, 2200.0], [5.0], lut=(rads, wave))
+
+
+def test_generate_template_matches_reference_golden_when_the_lut_is_present(golden):
+    """with the reference's ch4.hdr / ch4.lut at hand (build container) the 73-band AVIRIS template equals the one
+    the reference's own function produced (tests/golden/ch4_template_aviris.npz)"""
+    import os
+    import numpy as np
+    import pytest
+    from starcop_b200 import mag1c
+    lut_dir = os.environ.get("STARCOP_CH4_LUT_DIR", "/root/reference/starcop/models")
+    if not os.path.exists(os.path.join(lut_dir, "ch4.lut")):
+        pytest.skip("ch4.lut not available on this machine")
+    g = golden("ch4_template_aviris.npz")
+    rads, wave = mag1c.read_ch4_lut(lut_dir)
+    assert rads.shape == (7, 31800) and wave.shape == (31800,)
+    out = mag1c.generate_template_from_bands(g["centers"], g["fwhm"], lut_dir=lut_dir)
+    assert np.allclose(out, g["template"], rtol=1e-10, atol=0)
+    sl = mag1c.band_keep_aviris(g["wavelengths"])
+    assert (sl.start, sl.stop - 1) == (int(g["band_first"]), int(g["band_last"]))
