@@ -225,6 +225,13 @@ class UNetEngine:
         self._packed_this_step = False
         if not self._packs or not self._plan_complete:
             return
+        self._build_pack_table()
+        tab, n, total = self._pack_table[:3]
+        call("sc_tc_pack_weights_batch", tab.data_ptr(), n, total, self.stream)
+        self._packed_this_step = True
+
+    def _build_pack_table(self):
+        """device copy of the job table; built eagerly when the plan completes (never inside a graph capture)"""
         if self._pack_table is None:
             import numpy as np
             desc = np.zeros(len(self._packs), dtype=np.dtype([("w", "<u8"), ("out", "<u8"), ("offset", "<i8"), ("cout", "<i4"),
@@ -234,10 +241,8 @@ class UNetEngine:
             for i, (buf, d) in enumerate(self._packs.values()):
                 desc[i] = (d[0], d[1], off, d[2], d[3], d[4], d[5], d[6], d[7])
                 off += buf.numel()
-            self._pack_table = (torch.from_numpy(desc.view(np.uint8).copy()).to(self.device), len(self._packs), off)
-        tab, n, total = self._pack_table
-        call("sc_tc_pack_weights_batch", tab.data_ptr(), n, total, self.stream)
-        self._packed_this_step = True
+            host = torch.from_numpy(desc.view(np.uint8).copy()).pin_memory()      # pinned: the copy is legal even under capture
+            self._pack_table = (host.to(self.device, non_blocking=True), len(self._packs), off, host)
 
     def _halo_ok(self, x, cin, cout, k, stride):
         """thin 3x3 layers (decoder blocks 2-4): one staged halo patch per tile + resident weights (conv_tc_halo.cu)"""
@@ -455,3 +460,5 @@ class UNetEngine:
             fn()
         self.tape = []
         self._plan_complete = True          # every fprop and dgrad packing request of the network is now recorded
+        if self._packs and self._pack_table is None:
+            self._build_pack_table()
