@@ -123,6 +123,12 @@ int sc_head_fprop(const void* x, int ldx, const float* w, const float* bias, flo
 int sc_head_bwd(const void* x, int ldx, const float* w, const float* dlogits, void* dx, int lddx,
                 float* dw, float* dbias, int N, int H, int W, int C, int dtype, void* stream);
 
+/* the head's weight / bias gradient through the depthwise tile machinery (TMA halo-tile ring, per-CTA partial
+ * rows: deterministic, no global atomics); dw / dbias are ACCUMULATED.  C in {8,16,24,32,48,64}. */
+int64_t sc_head_wgrad_workspace_bytes(int C);
+int sc_head_wgrad_tiled(const void* x, int ldx, const float* dlogits, float* dw, float* dbias, float* workspace,
+                        int N, int H, int W, int C, int dtype, void* stream);
+
 /* ---- A3/A4/A6: weighted BCE + decisions + confusion counts in ONE pass ----------------------
  * (model_module.py:76-79 train, :115-135 val, :191-212 batch_with_preds; torchmetrics
  * ConfusionMatrix.update).  logits/y/w: n = B*HW f32 (w may be NULL = no weight_loss).

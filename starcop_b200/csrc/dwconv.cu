@@ -473,6 +473,132 @@ dw_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// segmentation-head wgrad (Conv2d(C -> 1, 3x3), C <= 64): dw[c][tap] = sum_p x[p+tap][c] * dl[p], dbias = sum dl.
+// Same machinery as the depthwise wgrad (TMA halo-tile ring, 72 tap sums per thread, one partial row per CTA);
+// the "dy" of every channel is the single-channel fp32 logit gradient, read straight from global memory.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int CVB>
+__global__ void __launch_bounds__(kDwThreads, 2)
+head_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ dl, float* __restrict__ partial,
+                       int H, int W, int C, DwTiles g, int ns, int stage_bytes) {
+  constexpr int TWP = 2;
+  using G = DwGeo<1, CVB, TWP>;
+  constexpr int NI = TWP + 2;
+  constexpr uint32_t kXBytes = G::TILE_ELEMS * sizeof(T);
+  extern __shared__ __align__(128) uint8_t dw_smem[];
+  DwRing ring = dw_ring_init(dw_smem, ns, stage_bytes);
+  const int tid = threadIdx.x;
+  const int cvl = tid % CVB, pl = tid / CVB;
+  const bool active = pl < G::PLn;
+  float acc[9][8];
+#pragma unroll
+  for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[tp][k] = 0.f;
+  float bsum = 0.f;
+  const int my_tiles = (g.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto issue = [&](int i) {
+    int n, th, tw;
+    dw_tile_coords(blockIdx.x + i * gridDim.x, g, n, th, tw);
+    const int slot = i % ns;
+    mbar_arrive_expect_tx(&ring.full[slot], kXBytes);
+    tma_load_4d(ring.bufs + (size_t)slot * stage_bytes, &tmX, 0, tw * G::TW - 1, th * G::TH - 1, n, &ring.full[slot]);
+  };
+  __syncthreads();
+  if (tid == 0) {
+    tma_prefetch_desc(&tmX);
+    for (int i = 0; i < ns && i < my_tiles; ++i) issue(i);
+  }
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int i = 0; i < my_tiles; ++i) {
+    int n, th, tw;
+    dw_tile_coords(blockIdx.x + i * gridDim.x, g, n, th, tw);
+    const T* tile = reinterpret_cast<const T*>(ring.bufs + (size_t)slot * stage_bytes);
+    mbar_wait(&ring.full[slot], phase);
+    if (active) {
+#pragma unroll 1
+      for (int it = pl; it < G::ITEMS; it += G::PLn) {
+        const int r = it / G::STRIPS, sw = it - r * G::STRIPS;
+        const int oh = th * G::TH + r, ow = tw * G::TW + sw * TWP;
+        float g2[TWP] = {0.f, 0.f};                   // this strip's logit gradients, zero outside the image
+        if (oh < H) {
+          const float* dp = dl + ((int64_t)n * H + oh) * W + ow;
+#pragma unroll
+          for (int j = 0; j < TWP; ++j)
+            if (ow + j < W) g2[j] = dp[j];
+        }
+        if (cvl == 0) bsum += g2[0] + g2[1];
+        const T* tp0 = tile + ((r * G::IW + sw * TWP) * CVB + cvl) * 8;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int c = 0; c < NI; ++c) {
+            const f8 v = load8<T>(tp0 + (kh * G::IW + c) * CVB * 8);
+#pragma unroll
+            for (int j = 0; j < TWP; ++j) {
+              const int kw = c - j;
+              if (kw >= 0 && kw < 3) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc[kh * 3 + kw][k] = fmaf(v.v[k], g2[j], acc[kh * 3 + kw][k]);
+              }
+            }
+          }
+      }
+    }
+    __syncthreads();
+    if (tid == 0 && i + ns < my_tiles) {
+      fence_proxy_async();
+      issue(i + ns);
+    }
+    if (++slot == ns) {
+      slot = 0;
+      phase ^= 1;
+    }
+  }
+  // deterministic block reduction, one tap at a time (+ the bias sum) through [pl][cvl][8] floats
+  float* red = reinterpret_cast<float*>(ring.bufs);
+  float* row = partial + (int64_t)blockIdx.x * (C * 9 + 1);
+#pragma unroll
+  for (int tp = 0; tp < 10; ++tp) {
+    __syncthreads();
+    if (active) {
+      float* mine = red + (pl * CVB + cvl) * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) mine[k] = tp < 9 ? acc[tp < 9 ? tp : 0][k] : (k == 0 ? bsum : 0.f);
+    }
+    __syncthreads();
+    for (int o = tid; o < CVB * 8; o += kDwThreads) {
+      float sv = 0.f;
+      for (int j = 0; j < G::PLn; ++j) sv += red[j * CVB * 8 + o];
+      if (tp < 9) row[o * 9 + tp] = sv;
+    }
+    if (tp == 9 && tid == 0) {
+      float sv = 0.f;
+      for (int j = 0; j < G::PLn * CVB; ++j) sv += red[j * 8];
+      row[C * 9] = sv;
+    }
+  }
+}
+
+__global__ void head_wgrad_sum_kernel(const float* __restrict__ partial, int nrows, int n, float* __restrict__ dw,
+                                      float* __restrict__ dbias) {
+  __shared__ float sh[32][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int i = blockIdx.x * 32 + tx;
+  float s = 0.f;
+  if (i <= n)
+    for (int r = ty; r < nrows; r += 32) s += partial[(int64_t)r * (n + 1) + i];
+  sh[ty][tx] = s;
+  __syncthreads();
+  if (ty != 0 || i > n) return;
+#pragma unroll
+  for (int j = 1; j < 32; ++j) s += sh[j][tx];
+  if (i < n) dw[i] += s;
+  else if (dbias) dbias[0] += s;
+}
+
 __global__ void dw_wgrad_sum_kernel(const float* __restrict__ partial, int nrows, int n, float* __restrict__ dw) {
   __shared__ float sh[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -655,6 +781,29 @@ static int launch_wgrad_cvb(const T* x, int ldx, const float* scale, const float
   return check_launch();
 }
 
+template <typename T, int CVB>
+static int launch_head_wgrad_cvb(const T* x, int ldx, const float* dl, float* dw, float* dbias, float* workspace, int N,
+                                 int H, int W, int C, cudaStream_t st) {
+  using G = DwGeo<1, CVB, 2>;
+  DwTiles g;
+  if (!dw_tiles(N, H, W, G::TH, G::TW, &g)) return SC_ERR_BAD_ARG;
+  const size_t stage = ((size_t)G::TILE_ELEMS * sizeof(T) + 127) & ~(size_t)127;
+  int ns = dw_ring_depth(stage, 64, 2);
+  if (ns < 1) return SC_ERR_UNSUPPORTED;
+  const int gx = dw_grid_x(g, 1, 2, kDwMaxRows);
+  size_t smem = 128 + (size_t)ns * stage + 64;
+  if (smem < (size_t)kDwThreads * 8 * sizeof(float) + 256) smem = (size_t)kDwThreads * 8 * sizeof(float) + 256;
+  CUtensorMap tmX;
+  if (!encode_nhwc_plain(&tmX, x, (int)sizeof(T), C, W, H, N, ldx, CVB * 8, G::IW, G::IH)) return SC_ERR_NO_DEVICE;
+  int rc = set_smem(head_wgrad_tile_kernel<T, CVB>, smem);
+  if (rc != SC_OK) return rc;
+  head_wgrad_tile_kernel<T, CVB><<<gx, kDwThreads, smem, st>>>(tmX, dl, workspace, H, W, C, g, ns, (int)stage);
+  rc = check_launch();
+  if (rc != SC_OK) return rc;
+  head_wgrad_sum_kernel<<<(C * 9 + 1 + 31) / 32, dim3(32, 32), 0, st>>>(workspace, gx, C * 9, dw, dbias);
+  return check_launch();
+}
+
 #define DW_DISPATCH_CVB(cvb, ...)                            \
   switch (cvb) {                                             \
     case 8: { constexpr int CVB = 8; __VA_ARGS__; } break;   \
@@ -733,6 +882,19 @@ extern "C" int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* d
     return check_launch();
   }
   SC_DISPATCH_DTYPE(dtype, return launch_dgrad_s2<T>((const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C, st));
+  return SC_ERR_BAD_ARG;
+}
+
+// head wgrad through the tile machinery: C in {8, 16, 24, 32, 48, 64} (all channels in one block)
+extern "C" int64_t sc_head_wgrad_workspace_bytes(int C) { return (int64_t)kDwMaxRows * (C * 9 + 1) * sizeof(float); }
+extern "C" int sc_head_wgrad_tiled(const void* x, int ldx, const float* dlogits, float* dw, float* dbias, float* workspace,
+                                   int N, int H, int W, int C, int dtype, void* stream) {
+  if (!x || !dlogits || !dw || !workspace || C % 8 || C > 64 || ldx % 8 || N <= 0) return SC_ERR_BAD_ARG;
+  const int cv = C / 8;
+  if (cv != 1 && cv != 2 && cv != 3 && cv != 4 && cv != 6 && cv != 8) return SC_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  SC_DISPATCH_DTYPE(dtype, DW_DISPATCH_CVB(cv, return (launch_head_wgrad_cvb<T, CVB>((const T*)x, ldx, dlogits, dw, dbias,
+                                                                                    workspace, N, H, W, C, st))));
   return SC_ERR_BAD_ARG;
 }
 

@@ -453,9 +453,12 @@ class UNetEngine:
         z = self._head_in
         z.grad = self.new_like(z)
         hw = self.p["segmentation_head.0.weight"]
-        call("sc_head_bwd", z.ptr, z.ld, hw.data_ptr(), dlogits_ptr, z.grad.ptr, z.grad.ld,
-             self.g["segmentation_head.0.weight"].data_ptr(), self.g["segmentation_head.0.bias"].data_ptr(),
+        # data gradient by the per-pixel kernel; weight / bias gradient by the TMA tile kernel (partial rows)
+        call("sc_head_bwd", z.ptr, z.ld, hw.data_ptr(), dlogits_ptr, z.grad.ptr, z.grad.ld, 0, 0,
              z.N, z.H, z.W, z.C, self.dtype, self.stream)
+        ws = self.arena.alloc(_lib.load().sc_head_wgrad_workspace_bytes(z.C))
+        call("sc_head_wgrad_tiled", z.ptr, z.ld, dlogits_ptr, self.g["segmentation_head.0.weight"].data_ptr(),
+             self.g["segmentation_head.0.bias"].data_ptr(), ws, z.N, z.H, z.W, z.C, self.dtype, self.stream)
         for fn in reversed(self.tape):
             fn()
         self.tape = []

@@ -206,6 +206,27 @@ def test_head(dtype):
     assert torch.allclose(db, gb, rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("dtype", [SC_F32, SC_BF16])
+@pytest.mark.parametrize("C,h,w", [(16, 32, 32), (16, 40, 24), (8, 19, 37), (64, 16, 16), (32, 64, 48)])
+def test_head_wgrad_tiled(dtype, C, h, w):
+    """weight / bias gradient of the head through the TMA tile kernel (ragged tiles, several channel-block widths);
+    dw / dbias are accumulated onto what is there"""
+    torch.manual_seed(4)
+    N = 3
+    x = nhwc(torch.randn(N, C, h, w, device=DEV), dtype)
+    xr = x.float().permute(0, 3, 1, 2)
+    conv = torch.nn.Conv2d(C, 1, 3, padding=1).to(DEV)
+    yr = conv(xr)
+    dl = torch.randn_like(yr)
+    gw, gb = torch.autograd.grad(yr, [conv.weight, conv.bias], dl)
+    dw, db = torch.ones_like(conv.weight), torch.full_like(conv.bias, 2.0)
+    ws = torch.empty(load().sc_head_wgrad_workspace_bytes(C) // 4, device=DEV)
+    call("sc_head_wgrad_tiled", x.data_ptr(), C, dl.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), N, h, w, C, dtype, st())
+    scale = gw.abs().max().item()
+    assert (dw - 1.0 - gw).abs().max().item() <= 2e-5 * scale + 1e-4
+    assert abs(db.item() - 2.0 - gb.item()) <= 1e-4 * max(1.0, abs(gb.item()))
+
+
 def test_add_into_pooled_and_accumulate():
     N, C, hw = 2, 24, 6
     a = torch.randn(N, 2 * hw, 2 * hw, C + 8, device=DEV)
