@@ -24,8 +24,6 @@
 //     TMEM accumulators): one tile's K loop is a dependent chain that leaves the pipe idle at N <= 80;
 //   * ALL taps' weights stay resident in shared memory for the CTA's lifetime ([K/8][Cout] granules).
 // Warp roles / TMEM double buffering / BatchNorm statistics epilogue as in conv_tc.cu.
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -50,7 +48,6 @@ struct HaloParams {
   int stages, ldy, accumulate;
   int batch, ncols;            // tiles per MMA batch, TMEM columns per accumulator
   int tmem_cols;               // allocation: power of two >= 2 * batch * ncols
-  int fence;
   __nv_bfloat16* y;
   const __nv_bfloat16* w;      // [Cout][9][np*8]
   const __nv_bfloat16* x;
@@ -195,7 +192,8 @@ tc_conv3x3_halo_kernel(HaloParams p) {
         }
         tc_fence_after();
         // the patches were written through the generic proxy (cp.async); UMMA reads through the async proxy
-        if (p.fence) fence_proxy_async();
+        // (measured: the fence costs < 2 % here)
+        fence_proxy_async();
         const uint32_t d_tmem = tmem_base + acc * (G * NP);
         uint32_t first = 0;
         for (int tap = 0; tap < 9; ++tap) {
@@ -396,14 +394,9 @@ extern "C" int sc_tc_conv3x3_halo(const void* x, int ldx, const void* w_bf16, vo
     }
   }
   if (!best_ctas) return SC_ERR_UNSUPPORTED;
-  if (const char* e = getenv("STARCOP_HALO_BATCH")) {
-    const int bb = atoi(e);
-    if (bb >= 1 && bb <= best_batch) best_batch = bb;
-  }
   const int stages = best_stages;
   p.stages = stages;
   p.batch = best_batch;
-  p.fence = getenv("STARCOP_HALO_NOFENCE") ? 0 : 1;     // timing experiment only
   p.tmem_cols = 32;
   while (p.tmem_cols < 2 * p.batch * p.ncols) p.tmem_cols *= 2;
   const size_t smem = halo_smem(p.np, Cout, stages, stats != nullptr);

@@ -1,0 +1,119 @@
+"""Parity at BASELINE.json's FULL sizes, where the CPU oracle is too slow to be the checker: size-independent
+properties instead -- two independent CUDA implementations of the same operator must agree, linearity,
+round trips -- on 512 x 512 tiles at the bench batch."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from starcop_b200 import features, mag1c, synthetic  # noqa: E402
+from starcop_b200._lib import ACT_RELU6, SC_BF16, call, load  # noqa: E402
+
+DEV = "cuda"
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def test_mag1c_resident_kernel_equals_streaming_kernel_on_full_tiles(monkeypatch):
+    """configs[2] shape: 512 x 512 x 125 cubes, 73-band window, 512 groups of 512 pixels per tile.  The resident
+    kernel (Woodbury updates of the inverse covariance) and the streaming kernel (covariance rebuild + Cholesky per
+    iteration) are different algorithms for the same fixed-point iteration: they must agree far inside the 3e-3
+    tolerance that pins either one to the reference."""
+    t73 = synthetic.synthetic_template(73)
+    cube, _, alpha = synthetic.aviris_cube(2, size=512, bands=125, seed=11, template=t73)
+    c = torch.from_numpy(cube).to(DEV)
+    sl = slice(52, 125)
+    for it in (0, 30):
+        mf_r, al_r = mag1c.mag1c_tiles(c, t73, sl, num_iter=it)
+        monkeypatch.setenv("STARCOP_MAG1C_STREAMING", "1")
+        mf_s, al_s = mag1c.mag1c_tiles(c, t73, sl, num_iter=it)
+        monkeypatch.delenv("STARCOP_MAG1C_STREAMING")
+        scale = mf_s.abs().max().item()
+        assert (mf_r - mf_s).abs().max().item() <= 2e-4 * scale, it
+        assert torch.allclose(al_r, al_s, rtol=1e-5)
+    # the injected plumes are recovered on the full tile
+    plume = torch.from_numpy(alpha[0] > 0).to(DEV)
+    assert mf_r[0][plume].mean() > 5 * mf_r[0][~plume].mean()
+    # scale covariance of the matched filter: radiance * k leaves the albedo-normalised output unchanged (rmf)
+    mf1, _ = mag1c.mag1c_tiles(c[:1], t73, sl, num_iter=0)
+    mf2, _ = mag1c.mag1c_tiles(c[:1] * 2.0, t73, sl, num_iter=0)
+    assert (mf1 - mf2).abs().max().item() <= 1e-4 * mf1.abs().max().item()
+
+
+@pytest.mark.parametrize("cin,cout", [(16, 16), (32, 16), (16, 32), (32, 32)])
+def test_halo_kernel_equals_per_tap_kernel_at_bench_shape(cin, cout):
+    """decoder block 3/4 geometries at bs 16: both tcgen05 kernels accumulate the same bf16 products in fp32, only
+    the summation order over the taps differs"""
+    lib = load()
+    N, H, W = 16, 256, 256
+    torch.manual_seed(5)
+    x = torch.randn(N, H, W, cin, device=DEV).to(torch.bfloat16)
+    w = torch.randn(cout, cin, 3, 3, device=DEV) / np.sqrt(9 * cin)
+    outs = []
+    for halo in (True, False):
+        cpad = lib.sc_tc_halo_cin_pad(cin) if halo else lib.sc_tc_cin_pad(cin)
+        wb = torch.empty(cout * 9 * cpad, device=DEV, dtype=torch.bfloat16)
+        call("sc_tc_pack_weights", w.data_ptr(), wb.data_ptr(), cout, cin, 3, 3, 0, cpad, cout, st())
+        y = torch.full((N, H, W, cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+        part = torch.zeros(lib.sc_bn_partials_bytes(cout) // 8, dtype=torch.float64, device=DEV)
+        n = ctypes.c_int(0)
+        if halo:
+            call("sc_tc_conv3x3_halo", x.data_ptr(), cin, wb.data_ptr(), y.data_ptr(), cout, part.data_ptr(), ctypes.byref(n),
+                 N, H, W, cin, cout, 0, st())
+        else:
+            call("sc_tc_conv_fprop", x.data_ptr(), cin, wb.data_ptr(), y.data_ptr(), cout, part.data_ptr(), ctypes.byref(n),
+                 N, H, W, cin, cout, 3, 3, 1, 0, st())
+        outs.append((y.float(), part[:n.value * 2 * cout].view(n.value, 2 * cout).sum(0)))
+    (ya, sa), (yb, sb) = outs
+    assert torch.isfinite(ya).all()
+    assert (ya - yb).abs().max().item() <= 2 ** -6 * max(1.0, yb.abs().max().item())      # <= 1-2 bf16 ulps
+    assert (ya != yb).float().mean().item() < 0.05                                        # and almost always identical
+    assert torch.allclose(sa, sb, rtol=1e-3, atol=1.0)
+    # a spot check of both against fp32 PyTorch on one image
+    ref = F.conv2d(x[:1].float().permute(0, 3, 1, 2), w.to(torch.bfloat16).float(), padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(ya[:1], ref.to(torch.bfloat16).float(), rtol=1.6e-2, atol=1e-3)
+
+
+def test_depthwise_linearity_and_adjointness_at_bench_shape():
+    """f2.dw (96 ch, 256^2 -> 128^2, stride 2) at bs 16: <dw(x), g> == <x, dw^T(g)> (fprop vs dgrad are adjoint) and
+    the weight gradient is the derivative of that bilinear form -- no oracle needed, any indexing slip breaks it"""
+    lib = load()
+    N, H, C, s = 16, 256, 96, 2
+    Ho = H // s
+    torch.manual_seed(6)
+    x = torch.randn(N, H, H, C, device=DEV).to(torch.bfloat16)
+    g = torch.randn(N, Ho, Ho, C, device=DEV).to(torch.bfloat16)
+    w = torch.randn(C, 1, 3, 3, device=DEV) / 3
+    y = torch.empty(N, Ho, Ho, C, device=DEV, dtype=torch.bfloat16)
+    dx = torch.empty(N, H, H, C, device=DEV, dtype=torch.bfloat16)
+    call("sc_dwconv_fprop", x.data_ptr(), C, 0, 0, 0, w.data_ptr(), y.data_ptr(), C, 0, 0, N, H, H, C, s, SC_BF16, st())
+    call("sc_dwconv_dgrad", g.data_ptr(), C, w.data_ptr(), dx.data_ptr(), C, N, H, H, C, s, SC_BF16, st())
+    lhs = (y.double() * g.double()).sum().item()
+    rhs = (x.double() * dx.double()).sum().item()
+    norm = (y.double().norm() * g.double().norm()).item()
+    assert abs(lhs - rhs) <= 2e-3 * norm, (lhs, rhs, norm)
+    dw = torch.zeros_like(w)
+    ws = torch.empty(lib.sc_dwconv_wgrad_workspace_bytes(C) // 4, device=DEV)
+    call("sc_dwconv_wgrad", x.data_ptr(), C, 0, 0, 0, g.data_ptr(), C, dw.data_ptr(), ws.data_ptr(), N, H, H, C, s, SC_BF16, st())
+    # <dw(x; w), g> is linear in w with gradient dw: evaluate it exactly
+    assert abs((dw.double() * w.double()).sum().item() - lhs) <= 2e-3 * norm
+
+
+def test_ratio_product_idempotent_structure_on_full_batch():
+    """16 tiles of 512^2: the cluster kernel's exact percentiles -- c rescales sig so that the inlier sums match,
+    hence applying the product to (bg, c*sig) must return c' = 1 to fp32 rounding"""
+    torch.manual_seed(7)
+    bg = torch.rand(16, 512, 512, device=DEV) * 2 + 0.5
+    sig = bg * 0.7 + 0.02 * torch.randn_like(bg)
+    r = features.ratio_2c_match_c_from_sums_outlier(bg, sig)
+    c = ((r * (bg + 1e-6) + bg) / sig).flatten(1).median(dim=1).values            # per-tile gain recovered from R
+    sig2 = sig * c[:, None, None]
+    r2 = features.ratio_2c_match_c_from_sums_outlier(bg, sig2)
+    c2 = ((r2 * (bg + 1e-6) + bg) / sig2).flatten(1).median(dim=1).values
+    assert torch.allclose(c2, torch.ones_like(c2), atol=2e-5)
