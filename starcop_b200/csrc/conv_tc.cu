@@ -166,6 +166,7 @@ struct FpropParams {
   int stages;
   int ldy;
   int accumulate;            // y += result (gradient fan-in)
+  int tmem_cols;             // 2 accumulator stages: 512, or 256 when two CTAs share an SM
   __nv_bfloat16* y;
   double* stats;             // optional [2][Cout] fp64 sum / sum of squares of the stored outputs
 };
@@ -174,7 +175,7 @@ constexpr int kTcThreads = 192;
 constexpr int kMaxDynSmem = 227 * 1024;
 
 template <int KC>
-__global__ void __launch_bounds__(kTcThreads, 1)
+__global__ void __launch_bounds__(kTcThreads, 2)
 tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, FpropParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -204,7 +205,7 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -265,7 +266,7 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * 256;
+        const uint32_t d_tmem = tmem_base + acc * (p.tmem_cols / 2);
         for (int si = 0; si < nstages_per_tile; ++si) {
           const int g_here = min(G, ksteps - si * G);
           mbar_wait(&full[stage], phase);
@@ -300,6 +301,9 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     }
     // after the recursive-halving reduction below, this lane owns column (lane >> 1) of each 16-column group
     const int my_col = lane >> 1;
+    // every 16-channel group of a pixel is a 32-byte aligned sector
+    const bool wide_ok = !p.accumulate && (p.ldy % 16) == 0 && (p.block_n % 16) == 0 &&
+                         (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -313,10 +317,28 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       tc_fence_after();
       int h = th * 8 + row / 16, w = tw * 16 + row % 16;
       __nv_bfloat16* yp = p.y + (((int64_t)img * p.H + h) * p.W + w) * p.ldy + n0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (p.tmem_cols / 2);
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);
+        if (wide_ok && n0 + c0 + 16 <= p.Cout) {
+          // 16 channels = one 32-byte sector per thread: ONE 256-bit store (STG.256) instead of two half-sector
+          // stores -- the wide 1x1 expansions are bound by these scattered stores, not by the MMAs
+          uint32_t w8[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w8[i] = *reinterpret_cast<uint32_t*>(&h2);
+            if (p.stats) {
+              const float2 f = __bfloat1622float2(h2);
+              v[2 * i] = f.x;
+              v[2 * i + 1] = f.y;
+            }
+          }
+          asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yp + c0), "r"(w8[0]), "r"(w8[1]), "r"(w8[2]),
+                       "r"(w8[3]), "r"(w8[4]), "r"(w8[5]), "r"(w8[6]), "r"(w8[7])
+                       : "memory");
+        } else
         // channels are handled in 8-wide halves (Cout % 8 == 0; a ragged last N tile is masked)
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -392,7 +414,7 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, p.tmem_cols);
   }
 }
 
@@ -442,7 +464,14 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
   p.groups = groups;
   const int stage_bytes = groups * group_bytes;
   const int tail = 1024 + 256 + (stats ? 2 * Cout * 4 : 0);   // alignment slack + barriers + statistics
-  int stages = (200 * 1024 - tail) / stage_bytes;
+  // Short-K layers (the 1x1 expansions / projections: one or two MMAs per tile) are bound by the per-tile
+  // TMA -> MMA -> epilogue hand-offs, not by the tensor pipe: run TWO CTAs per SM (half the shared memory,
+  // 256 TMEM columns each) so twice as many tiles are in flight.
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  bool two_cta = Cin * KH * KW <= 192 && p.block_n <= 128 && total_tiles >= 4 * kNumSMs;
+  if (two_cta && (100 * 1024 - tail) / stage_bytes < 3) two_cta = false;     // not enough pipeline depth in half an SM
+  p.tmem_cols = two_cta ? 256 : 512;
+  int stages = ((two_cta ? 100 : 200) * 1024 - tail) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return SC_ERR_UNSUPPORTED;
   p.stages = stages;
@@ -454,7 +483,8 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
   rc = encode_mat(&tmB, w_bf16, (int64_t)KH * KW * p.cchunks * kc, Cout, kc, p.block_n);
   if (rc != SC_OK) return rc;
   int total = p.m_tiles * p.n_tiles;
-  int grid = total < kNumSMs ? total : kNumSMs;
+  const int slots = two_cta ? 2 * kNumSMs : kNumSMs;
+  int grid = total < slots ? total : slots;
   if (stats) *stats_rows_host = grid;
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FPROP(KC)                                                                                     \
