@@ -225,6 +225,7 @@ tc_conv3x3_halo_kernel(HaloParams p) {
     const int my_col = lane >> 1;
     const int G = p.batch, NP = p.ncols;
     const int my_tiles = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool wide_ok = !p.accumulate && (p.ldy % 16) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
     int it = 0;
     for (int t0 = 0; t0 < my_tiles; t0 += G, ++it) {
       const int gn = my_tiles - t0 < G ? my_tiles - t0 : G;
@@ -262,7 +263,25 @@ tc_conv3x3_halo_kernel(HaloParams p) {
         for (int i = 0; i < 16; ++i) sv[i] = sq[i] = 0.f;
 #pragma unroll
         for (int g = 0; g < kMaxBatch; ++g) {
-          if (g < gn && valid[g]) {
+          if (g < gn && valid[g] && wide_ok) {
+            // 16 channels = one 32-byte sector: a single 256-bit store
+            uint32_t w8[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[g][2 * i]), __uint_as_float(r[g][2 * i + 1]));
+              w8[i] = *reinterpret_cast<uint32_t*>(&h2);
+              if (p.stats) {
+                const float2 f = __bfloat1622float2(h2);
+                sv[2 * i] += f.x;
+                sv[2 * i + 1] += f.y;
+                sq[2 * i] = fmaf(f.x, f.x, sq[2 * i]);
+                sq[2 * i + 1] = fmaf(f.y, f.y, sq[2 * i + 1]);
+              }
+            }
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yp[g] + c0), "r"(w8[0]), "r"(w8[1]),
+                         "r"(w8[2]), "r"(w8[3]), "r"(w8[4]), "r"(w8[5]), "r"(w8[6]), "r"(w8[7])
+                         : "memory");
+          } else if (g < gn && valid[g]) {
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               float vv[8];
