@@ -350,7 +350,7 @@ __host__ __device__ inline int res_sp(int S) { return (S + 7) / 8 * 8; }
 __host__ __device__ inline int res_lda(int S) { return S | 1; }
 __host__ __device__ inline size_t res_smem_bytes(int S) {
   const int SP = res_sp(S);
-  return (size_t)(S * res_lda(S) + 14 * SP + kResMaxP + 64) * 8 + (size_t)SP * kResLdx * 4 + kResMaxP * 4 + 16;
+  return (size_t)(S * res_lda(S) + 1 + 14 * SP + kResMaxP + 64) * 8 + (size_t)SP * kResLdx * 4 + kResMaxP * 4 + 16;
 }
 
 __global__ void __launch_bounds__(kResThreads, 1)
@@ -365,7 +365,7 @@ mag1c_resident_kernel(const float* __restrict__ x, int64_t pixel_stride, const i
   const int32_t* idx = pix_idx + (int64_t)g * pmax;
   const int SP = res_sp(S), LDA = res_lda(S);
   double* A = smd;                       // S x LDA: C0, then P0 = C0^-1
-  double* xbar = A + S * LDA;
+  double* xbar = A + ((S * LDA + 1) & ~1);     // vectors 16-byte aligned (double2 loads of cit / xbar)
   double* tp = xbar + SP;                // template
   double* tprev = tp + SP;               // t: target inside modx
   double* tcur = tprev + SP;             // b: target = template * mu
@@ -392,6 +392,10 @@ mag1c_resident_kernel(const float* __restrict__ x, int64_t pixel_stride, const i
   for (int i = tid; i < P; i += kResThreads) pidx[i] = idx[i];
   for (int i = tid; i < S; i += kResThreads) tp[i] = tmpl[i];
   for (int i = tid; i < (SP - S) * kResLdx; i += kResThreads) Xt[(size_t)S * kResLdx + i] = 0.f;   // pad bands
+  if (P < kResMaxP) {                                                                               // pad pixels
+    const int npad = kResMaxP - P;
+    for (int i = tid; i < S * npad; i += kResThreads) Xt[(size_t)(i / npad) * kResLdx + P + i % npad] = 0.f;
+  }
   __syncthreads();
 
   // ---- the ONE pass over HBM: pixel-major global -> band-major shared.  One warp per pixel, lanes over bands:
@@ -615,10 +619,13 @@ mag1c_resident_kernel(const float* __restrict__ x, int64_t pixel_stride, const i
       double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
       int s2 = 0;
       for (; s2 + 4 <= S; s2 += 4) {
-        d0 = fma((double)(xp[(size_t)s2 * kResLdx]), cit[s2], d0);
-        d1 = fma((double)(xp[(size_t)(s2 + 1) * kResLdx]), cit[s2 + 1], d1);
-        d2 = fma((double)(xp[(size_t)(s2 + 2) * kResLdx]), cit[s2 + 2], d2);
-        d3 = fma((double)(xp[(size_t)(s2 + 3) * kResLdx]), cit[s2 + 3], d3);
+        // the filter coefficients are warp-uniform: two 16-byte broadcast loads per four bands
+        const double2 c01 = *reinterpret_cast<const double2*>(cit + s2);
+        const double2 c23 = *reinterpret_cast<const double2*>(cit + s2 + 2);
+        d0 = fma((double)(xp[(size_t)s2 * kResLdx]), c01.x, d0);
+        d1 = fma((double)(xp[(size_t)(s2 + 1) * kResLdx]), c01.y, d1);
+        d2 = fma((double)(xp[(size_t)(s2 + 2) * kResLdx]), c23.x, d2);
+        d3 = fma((double)(xp[(size_t)(s2 + 3) * kResLdx]), c23.y, d3);
       }
       for (; s2 < S; ++s2) d0 = fma((double)(xp[(size_t)s2 * kResLdx]), cit[s2], d0);
       const double dot = (d0 + d1) + (d2 + d3);
@@ -663,13 +670,22 @@ mag1c_resident_kernel(const float* __restrict__ x, int64_t pixel_stride, const i
       sum_a += scal[8 + wq];
       sum_a2 += scal[8 + NW + wq];
     }
-    // v = X^T a: one warp per band
-    for (int s2 = warp; s2 < S; s2 += NW) {
-      const float* row = Xt + (size_t)s2 * kResLdx;
-      double acc = 0.0;
-      for (int p = lane; p < P; p += 32) acc = fma((double)(row[p]), a_s[p], acc);
-      acc = warp_sum_all(acc);
-      if (lane == 0) v[s2] = acc;
+    // v = X^T a: one warp per band; each lane keeps its 16 pixels' a in registers across the warp's bands
+    {
+      double ar[kResMaxP / 32];
+#pragma unroll
+      for (int k = 0; k < kResMaxP / 32; ++k) ar[k] = lane + 32 * k < P ? a_s[lane + 32 * k] : 0.0;
+      for (int s2 = warp; s2 < S; s2 += NW) {
+        const float* row = Xt + (size_t)s2 * kResLdx + lane;
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < kResMaxP / 32; k += 2) {
+          acc0 = fma((double)row[32 * k], ar[k], acc0);             // pad pixels are zero-filled and meet a = 0
+          acc1 = fma((double)row[32 * (k + 1)], ar[k + 1], acc1);
+        }
+        const double acc = warp_sum_all(acc0 + acc1);
+        if (lane == 0) v[s2] = acc;
+      }
     }
     __syncthreads();
   }
