@@ -1,7 +1,10 @@
 // Bandwidth-bound kernels of the STARCOP hot path: input normalisation, training-mode BatchNorm
 // (statistics / finalize / apply / backward), gradient routing, segmentation head, fused weighted
 // BCE + decisions + confusion counts, Adam.  All NHWC, 8-channel vectors, fp32 math, fp64 sums.
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace sc {
 thread_local cudaError_t g_last_error = cudaSuccess;
@@ -400,12 +403,135 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const T* __restri
   }
 }
 
+// Flat variant for the dense full-resolution layers (C in {16, 32, 64}, dz and y contiguous): both tensors are
+// plain arrays, so a CTA streams them through shared memory with 1-D bulk copies (cp.async.bulk, a ring of
+// three chunks in flight) instead of holding every in-flight byte in registers -- the register-bound kernel
+// above tops out at ~2.8 TB/s on these layers with the 296-CTA cap of the partial-row protocol.
+constexpr int kFlatThreads = 256;
+constexpr int kFlatStages = 3;
+constexpr int kFlatPixPerThread = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(kFlatThreads, 2)
+bn_bwd_reduce_flat_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ scale,
+                          const float* __restrict__ shift, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, int act, double* __restrict__ partials, int64_t P, int C) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  const int CV = C / 8, PL = kFlatThreads / CV;
+  const int PPC = PL * kFlatPixPerThread;                         // pixels per chunk
+  const uint32_t chunk_bytes = (uint32_t)PPC * C * sizeof(T);     // per tensor
+  T* bufs = reinterpret_cast<T*>(fsm);                            // [stage][2][PPC*C]
+  uint64_t* full = reinterpret_cast<uint64_t*>(fsm + (size_t)kFlatStages * 2 * chunk_bytes);
+  double* sm = reinterpret_cast<double*>(fsm);          // [PL][CV][16] reduction scratch, aliases the (drained) ring
+  const int tid = threadIdx.x, cv = tid % CV, pl = tid / CV;
+  const int64_t nchunks = (P + PPC - 1) / PPC;
+  const int64_t my_n = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+    for (int i = 0; i < kFlatStages; ++i) tc::mbar_init(&full[i], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t i) {
+    const int64_t c = blockIdx.x + i * gridDim.x;
+    const int64_t p0 = c * PPC;
+    const int64_t np = P - p0 < PPC ? P - p0 : PPC;
+    const uint32_t bytes = (uint32_t)(np * C * sizeof(T));
+    const int slot = (int)(i % kFlatStages);
+    T* b = bufs + (size_t)slot * 2 * PPC * C;
+    tc::mbar_arrive_expect_tx(&full[slot], 2 * bytes);
+    tc::bulk_load_1d(b, y + p0 * C, bytes, &full[slot]);
+    tc::bulk_load_1d(b + (size_t)PPC * C, dz + p0 * C, bytes, &full[slot]);
+  };
+  if (tid == 0)
+    for (int i = 0; i < kFlatStages && i < my_n; ++i) issue(i);
+  const f8 sc_ = load8<float>(scale + cv * 8), sh = load8<float>(shift + cv * 8);
+  const f8 mu = load8<float>(mean + cv * 8), is = load8<float>(invstd + cv * 8);
+  double s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t i = 0; i < my_n; ++i) {
+    const int64_t p0 = (blockIdx.x + i * gridDim.x) * PPC;
+    const T* by = bufs + (size_t)slot * 2 * PPC * C;
+    const T* bg = by + (size_t)PPC * C;
+    tc::mbar_wait(&full[slot], phase);
+    float fs[8], fq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fs[k] = fq[k] = 0.f;
+#pragma unroll
+    for (int u = 0; u < kFlatPixPerThread; ++u) {
+      const int pp = pl + u * PL;
+      if (p0 + pp < P) {
+        const f8 yv = load8<T>(by + (size_t)pp * C + cv * 8);
+        const f8 g = load8<T>(bg + (size_t)pp * C + cv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float gi = g.v[k] * act_mask(fmaf(yv.v[k], sc_.v[k], sh.v[k]), act);
+          const float xh = (yv.v[k] - mu.v[k]) * is.v[k];
+          fs[k] += gi;
+          fq[k] = fmaf(gi, xh, fq[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] += (double)fs[k];
+      q[k] += (double)fq[k];
+    }
+    __syncthreads();                                  // every reader of the slot is done
+    if (tid == 0 && i + kFlatStages < my_n) issue(i + kFlatStages);
+    if (++slot == kFlatStages) {
+      slot = 0;
+      phase ^= 1;
+    }
+  }
+  double* mine = sm + ((size_t)pl * CV + cv) * 16;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mine[k] = s[k];
+    mine[8 + k] = q[k];
+  }
+  __syncthreads();
+  double* row = partials + (int64_t)blockIdx.x * 2 * C;
+  for (int o = tid; o < CV * 16; o += kFlatThreads) {
+    const int cvo = o / 16, k = o % 16;
+    double t = 0.0;
+    for (int j = 0; j < PL; ++j) t += sm[((size_t)j * CV + cvo) * 16 + k];
+    row[(k < 8 ? 0 : C) + cvo * 8 + (k & 7)] = t;
+  }
+}
+
 extern "C" int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void* y, int ldy,
                                 const float* scale, const float* shift, const float* mean,
                                 const float* invstd, int act, double* red, int* nrows_host, int N, int H, int W,
                                 int C, int dtype, void* stream) {
   if (!dz || !y || !red || !nrows_host || C % 8 || ldy % 8 || lddz % 8) return SC_ERR_BAD_ARG;
   int64_t P = (int64_t)N * H * W;
+  if (!pooled && lddz == C && ldy == C && (C == 16 || C == 32 || C == 64) && P >= (int64_t)1 << 18 &&
+      !(reinterpret_cast<uintptr_t>(dz) & 15) && !(reinterpret_cast<uintptr_t>(y) & 15) && !getenv("STARCOP_BN_NOFLAT")) {
+    const int esz = dtype == SC_F32 ? 4 : 2;
+    const int PPC = (kFlatThreads / (C / 8)) * kFlatPixPerThread;
+    const size_t smem = (size_t)kFlatStages * 2 * PPC * C * esz + 64;      // >= 32 KB: also the reduction scratch
+    const int64_t nchunks = (P + PPC - 1) / PPC;
+    const int gx = (int)(nchunks < SC_BN_MAX_PARTIALS ? nchunks : SC_BN_MAX_PARTIALS);
+    *nrows_host = gx;
+    cudaError_t e;
+    if (dtype == SC_F32) {
+      e = cudaFuncSetAttribute(bn_bwd_reduce_flat_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
+      bn_bwd_reduce_flat_kernel<float><<<gx, kFlatThreads, smem, (cudaStream_t)stream>>>(
+          (const float*)dz, (const float*)y, scale, shift, mean, invstd, act, red, P, C);
+    } else if (dtype == SC_BF16) {
+      e = cudaFuncSetAttribute(bn_bwd_reduce_flat_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
+      bn_bwd_reduce_flat_kernel<__nv_bfloat16><<<gx, kFlatThreads, smem, (cudaStream_t)stream>>>(
+          (const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, scale, shift, mean, invstd, act, red, P, C);
+    } else {
+      return SC_ERR_BAD_ARG;
+    }
+    return check_launch();
+  }
   RedGeom g = red_geom(C);
   dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
   *nrows_host = (int)grid.x;

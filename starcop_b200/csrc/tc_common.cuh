@@ -66,6 +66,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, int
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (no tensor map): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- TMEM allocation (one warp, .sync.aligned) ------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols)

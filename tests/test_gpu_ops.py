@@ -120,7 +120,10 @@ def test_depthwise(dtype, c, stride, hw, fused):
 @pytest.mark.parametrize("dtype", [SC_F32, SC_BF16])
 @pytest.mark.parametrize("c,hw,act,up2,res", [(16, 16, ACT_RELU6, False, False), (96, 8, ACT_NONE, False, True),
                                               (1280, 2, ACT_RELU6, True, False), (32, 16, ACT_RELU, True, False),
-                                              (2064, 2, ACT_RELU, False, False)])
+                                              (2064, 2, ACT_RELU, False, False),
+                                              # >= 2^18 pixels, contiguous, C in {16, 32, 64}: the bulk-copy ("flat")
+                                              # backward-reduce kernel, with a ragged last chunk
+                                              (16, 304, ACT_RELU, False, False), (64, 300, ACT_RELU6, False, False)])
 def test_batchnorm_train_forward_backward(dtype, c, hw, act, up2, res):
     torch.manual_seed(2)
     N = 3
