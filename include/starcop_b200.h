@@ -12,6 +12,12 @@
  *   - there is no CPU fallback anywhere behind this header.
  *
  * Each entry point cites the reference call it replaces (paths relative to the STARCOP tree).
+ *
+ * Implementation selectors (environment, read per call; the tests use them to check two independent kernels of
+ * one operator against each other -- they never select a CPU path, there is none):
+ *   STARCOP_MAG1C_STREAMING  sc_mag1c_filter: always the streaming kernel (no group-resident fast path)
+ *   STARCOP_RATIO_NOCLUSTER / STARCOP_RATIO_CLUSTER   sc_ratio_product: force the single-CTA / the cluster select
+ *   STARCOP_BN_NOFLAT        sc_bn_bwd_reduce: always the register-streaming kernel (no cp.async.bulk ring)
  */
 #ifndef STARCOP_B200_H
 #define STARCOP_B200_H
