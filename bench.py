@@ -167,7 +167,18 @@ def run_reference(args, rank):
             "config": {"workload": f"HyperSTARCOP U-Net train step, {args.size}x{args.size}x4 tiles (CPU PyTorch fp32)"},
             "cpu_baseline": {"value": rate, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+def emit(line):
+    """the ONE JSON line goes to the real stdout; everything else this process (or a library under it: the NCCL
+    version banner, torch warnings) prints is routed to stderr"""
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 
 def main():
@@ -316,7 +327,7 @@ def main():
             "unet_tflops": value * UNET_TRAIN_GFLOP_PER_TILE / 1e3,
             "roofline": roof, "cpu_baseline": cpu, "spectral_products": spectral,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         # The captured CUDA graphs hold NCCL work: destroying the communicator (or normal interpreter teardown)
         # with them alive was observed to hang forever AFTER the result line was printed.  Quiesce, agree that
