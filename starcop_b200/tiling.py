@@ -34,6 +34,40 @@ def has_plume(label):
     return frac_positives(label) > (10 / 64 ** 2)
 
 
+def tiled_records(records, labels, tile_size, overlap, scene_shape=(512, 512)):
+    """``tiled_dataframe`` (datamodule.py:17-64) without pandas / georeader: every record (a dict with at least
+    ``"id"``) is expanded into one record per window of ``create_windows(scene_shape, tile_size, overlap)``;
+    ``labels[i]`` is record i's (H, W) binary label, from which each tile's ``frac_positives`` and
+    ``has_plume = frac_positives > 10 / 64**2`` are computed.  The tile keeps the original id in ``id_original``
+    and gets ``id = f"{id}_r{row}_c{col}_w{w}_h{h}"`` plus the four ``window_*`` fields."""
+    out = []
+    wins = create_windows(scene_shape, tile_size, overlap, include_incomplete=False)
+    for rec, lab in zip(records, labels):
+        lab = np.asarray(lab.cpu() if torch.is_tensor(lab) else lab)
+        for (r, c, h, w) in wins:
+            t = {k: v for k, v in rec.items() if k not in ("window_row_off", "window_col_off", "window_width", "window_height")}
+            tile = lab[..., r:r + h, c:c + w]
+            t["window"] = (r, c, h, w)
+            t["frac_positives"] = float(tile.sum()) / float(tile.size)
+            t["has_plume"] = t["frac_positives"] > (10 / 64 ** 2)
+            t["window_col_off"], t["window_row_off"], t["window_width"], t["window_height"] = c, r, w, h
+            t["id_original"] = rec["id"]
+            t["id"] = tile_id(rec["id"], (r, c, h, w))
+            out.append(t)
+    return out
+
+
+def add_sample_weight(has_plume_flags):
+    """datamodule.py:309-315: inverse-frequency weights for the WeightedRandomSampler --
+    1 / plume_fraction for plume tiles, 1 / (1 - plume_fraction) for the others (float64, like pandas)."""
+    flags = np.asarray(has_plume_flags).astype(bool)
+    plume_fraction = np.sum(flags) / flags.shape[0]
+    with np.errstate(divide="ignore"):
+        plume_weight = 1 / plume_fraction
+        non_plume_weight = 1 / (1 - plume_fraction)
+    return np.where(flags, plume_weight, non_plume_weight)
+
+
 def find_padding(v, divisor=8):
     """padding.py:5-10."""
     v_divisible = max(divisor, int(divisor * np.ceil(v / divisor)))

@@ -127,3 +127,34 @@ def test_generate_template_matches_reference_golden_when_the_lut_is_present(gold
     assert np.allclose(out, g["template"], rtol=1e-10, atol=0)
     sl = mag1c.band_keep_aviris(g["wavelengths"])
     assert (sl.start, sl.stop - 1) == (int(g["band_first"]), int(g["band_last"]))
+
+
+def test_tiled_records_and_sample_weights():
+    """A15: datamodule.py:17-64 (tiling of the 512 x 512 scenes, has_plume, id format) and :309-315 (sampler weights)"""
+    import numpy as np
+    from starcop_b200 import tiling
+    lab = np.zeros((2, 512, 512), np.float32)
+    lab[0, 64:128, 64:128] = 1                     # 4096 positives, inside tiles r0/r64 x c0/c64
+    lab[1, 0:3, 0:3] = 1                           # 9 px: 9/128^2 < 10/64^2 -> no plume anywhere
+    recs = [{"id": "ang1", "window_row_off": 0, "window_col_off": 0, "window_width": 512, "window_height": 512, "qplume": 1.0},
+            {"id": "ang2", "window_row_off": 0, "window_col_off": 0, "window_width": 512, "window_height": 512, "qplume": 0.0}]
+    tiles = tiling.tiled_records(recs, lab, (128, 128), (64, 64))
+    assert len(tiles) == 2 * 49                    # 7 x 7 windows per scene (the notebook's 441 = 9 x 49)
+    t = {x["id"]: x for x in tiles}
+    assert "ang1_r0_c0_w128_h128" in t and t["ang1_r64_c64_w128_h128"]["id_original"] == "ang1"
+    a = t["ang1_r64_c64_w128_h128"]
+    assert a["frac_positives"] == 4096 / 128 ** 2 and a["has_plume"] is True and a["qplume"] == 1.0
+    assert (a["window_row_off"], a["window_col_off"], a["window_width"], a["window_height"]) == (64, 64, 128, 128)
+    assert t["ang1_r0_c0_w128_h128"]["frac_positives"] == 4096 / 128 ** 2       # the blob sits in all four overlapping tiles
+    assert t["ang1_r128_c128_w128_h128"]["has_plume"] is False
+    assert not any(x["has_plume"] for x in tiles if x["id_original"] == "ang2")
+    flags = np.array([x["has_plume"] for x in tiles])
+    n_plume = int(flags.sum())
+    assert n_plume == 4
+    w = tiling.add_sample_weight(flags)
+    assert np.allclose(w[flags], len(tiles) / n_plume) and np.allclose(w[~flags], len(tiles) / (len(tiles) - n_plume))
+    assert abs(w[flags].sum() - w[~flags].sum()) < 1e-9      # both classes get the same total sampling mass
+    # whole-tile mode (tile = scene): one window, has_plume of the full label
+    whole = tiling.tiled_records(recs, lab, (512, 512), (0, 0))
+    assert [x["id"] for x in whole] == ["ang1_r0_c0_w512_h512", "ang2_r0_c0_w512_h512"]
+    assert whole[0]["has_plume"] is True and whole[1]["has_plume"] is False
