@@ -42,3 +42,56 @@ def default_settings(input_products=None, pos_weight=1.0, lr=1e-4, use_weight_lo
         model=Namespace(**model),
         training=Namespace(accelerator="gpu", devices=1, max_epochs=15, val_check_interval=.5),
     )
+
+
+def from_dict(d):
+    """nested dict (a parsed config.yaml) -> nested Namespace; lists stay lists"""
+    if isinstance(d, dict):
+        return Namespace(**{k: from_dict(v) for k, v in d.items()})
+    return d
+
+
+def to_dict(ns):
+    if isinstance(ns, SimpleNamespace):
+        return {k: to_dict(v) for k, v in ns.__dict__.items()}
+    return ns
+
+
+def load_settings(yaml_path=None, overrides=()):
+    """The reference builds its settings with hydra from ``scripts/configs/config.yaml`` plus ``key=value``
+    command-line overrides (scripts/train.py:23-26, bash/bash_train_example.sh).  Same result without hydra /
+    omegaconf: the YAML (or ``default_settings()`` when no path is given) with dotted overrides applied; values are
+    parsed as YAML scalars / lists (``model.pos_weight=1``, ``dataset.input_products=[mag1c,TOA_AVIRIS_640nm]``).
+    Like hydra, overriding a key that does not exist is an error unless it is prefixed with ``+``; the ``hydra:``
+    block of the file is dropped."""
+    import yaml
+    if yaml_path is None:
+        cfg = to_dict(default_settings())
+    else:
+        with open(yaml_path) as f:
+            cfg = yaml.safe_load(f)
+        cfg.pop("hydra", None)
+    for ov in overrides:
+        if "=" not in ov:
+            raise ValueError(f"override {ov!r} is not of the form key=value")
+        key, val = ov.split("=", 1)
+        add = key.startswith("+")
+        key = key.lstrip("+")
+        node = cfg
+        parts = key.split(".")
+        for part in parts[:-1]:
+            if part not in node:
+                if not add:
+                    raise KeyError(f"override {ov!r}: no such config group {part!r} (prefix the key with + to add it)")
+                node[part] = {}
+            node = node[part]
+        if parts[-1] not in node and not add:
+            raise KeyError(f"override {ov!r}: no such key (prefix it with + to add it)")
+        v = yaml.safe_load(val)
+        if isinstance(v, str):                   # PyYAML reads "1e-4" as a string; hydra's grammar reads a float
+            try:
+                v = float(v) if any(ch in v.lower() for ch in ".e") else int(v)
+            except ValueError:
+                pass
+        node[parts[-1]] = v
+    return from_dict(cfg)

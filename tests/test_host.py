@@ -179,3 +179,30 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert k in d, k
+
+
+def test_load_settings_yaml_and_hydra_style_overrides(tmp_path):
+    """scripts/train.py's settings without hydra: the reference's own config.yaml (when at hand) or a copy of its
+    structure, plus key=value overrides as in bash/bash_train_example.sh"""
+    import os
+    import pytest
+    from starcop_b200 import settings as st
+    ref = "/root/reference/scripts/configs/config.yaml"
+    if os.path.exists(ref):
+        s = st.load_settings(ref, ["model.pos_weight=1", "experiment_name=HyperSTARCOP_magic_rgb",
+                                   "dataset.input_products=[mag1c,TOA_AVIRIS_640nm,TOA_AVIRIS_550nm,TOA_AVIRIS_460nm]"])
+        assert s.model.pos_weight == 1 and s.model.lr == 0.0001 and s.model.semseg_backbone == "mobilenet_v2"
+        assert s.dataset.input_products == st.HYPERSTARCOP_PRODUCTS and s.dataset.use_weight_loss is True
+        assert "use_weight_loss" in s.dataset and "hydra" not in s and s.dataloader.batch_size == 32
+        assert s.dataset.training_size == [128, 128] and s.experiment_name == "HyperSTARCOP_magic_rgb"
+    y = tmp_path / "c.yaml"
+    y.write_text("model:\n  lr: 0.001\n  pos_weight: 15\ndataset:\n  input_products: [a, b]\nhydra:\n  job: {chdir: true}\n")
+    s = st.load_settings(str(y), ["model.lr=1e-4", "+model.compute_dtype=bf16", "dataset.input_products=[mag1c]"])
+    assert s.model.lr == 1e-4 and s.model.compute_dtype == "bf16" and s.dataset.input_products == ["mag1c"]
+    assert "hydra" not in s
+    with pytest.raises(KeyError):
+        st.load_settings(str(y), ["model.nope=1"])
+    with pytest.raises(ValueError):
+        st.load_settings(str(y), ["model.lr"])
+    d = st.load_settings(None, ["model.pos_weight=15"])
+    assert d.model.pos_weight == 15 and d.dataset.input_products == st.HYPERSTARCOP_PRODUCTS
