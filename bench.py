@@ -39,6 +39,8 @@ def parse():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spectral", action="store_true", help="skip the spectral-product (mag1c / ratio) timings")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the PyTorch-eager-on-GPU baseline legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip parity / per-kernel roofline table legs")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of one CUDA graph")
     ap.add_argument("--profile", action="store_true",
                     help="profiling run (under ncu): 1 warm-up, no e2e loop, no roofline probe; prints no bench line")
@@ -85,9 +87,9 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_reference_step_rate(size, steps, warmup, tiles=2):
+def cpu_reference_step_rate(size, steps, warmup, tiles=2, stat="median"):
     """Reference CPU path (oracle port of the reference's PyTorch fp32 module, all host threads):
-    fwd + loss + bwd + Adam on a bounded sample of `tiles` tiles per step."""
+    fwd + loss + bwd + Adam on `tiles` tiles per step; `warmup` untimed + `steps` timed steps."""
     from oracle.module import get_model as oracle_get_model
     from starcop_b200 import synthetic
     from starcop_b200.settings import default_settings
@@ -107,8 +109,137 @@ def cpu_reference_step_rate(size, steps, warmup, tiles=2):
         if i >= warmup:
             ts.append(time.perf_counter() - t0)
     ts.sort()
-    med = ts[len(ts) // 2]
-    return tiles / med, med, torch.get_num_threads(), f"{tiles} tiles of {size}x{size}x4 per step, {steps} timed steps, median"
+    t = ts[len(ts) // 2] if stat == "median" else sum(ts) / len(ts)
+    return tiles / t, t, torch.get_num_threads(), f"{tiles} tiles of {size}x{size}x4 per step, {warmup} warm-up + {steps} timed steps, {stat}"
+
+
+def gpu_eager_baseline(dev, B, S, steps=5, warmup=3):
+    """The reference's own GPU path is PyTorch eager (model_module.py:238-251 -> cuDNN): the same module (oracle
+    restatement of smp.Unet(mobilenet_v2) + BCE + Adam) on this B200, fp32 as the reference trains (TF32 off and
+    on) and bf16 autocast + channels_last -- BASELINE.md B4, SURVEY 8(d) "the real bar".  A reported baseline."""
+    from oracle.module import get_model as oracle_get_model
+    from oracle import loss_metrics as lm
+    from oracle.normalizer import normalize_x
+    from starcop_b200 import synthetic
+    from starcop_b200.settings import default_settings
+    out = {}
+    batch = synthetic.hyperstarcop_batch(B, size=S, seed=0)
+    x = normalize_x(batch["input"], default_settings().dataset.input_products).to(dev)
+    y, w = batch["output"].to(dev), batch["weight_loss"].to(dev)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    for name, tf32, autocast in (("fp32", False, False), ("fp32_tf32", True, False), ("bf16_autocast_channels_last", True, True)):
+        try:
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = True
+            torch.manual_seed(0)
+            m = oracle_get_model(default_settings(pos_weight=1.0)).to(dev).train()
+            net = m.network
+            xin = x
+            if autocast:
+                net = net.to(memory_format=torch.channels_last)
+                xin = x.contiguous(memory_format=torch.channels_last)
+            opt = torch.optim.Adam(net.parameters(), 1e-4, fused=True)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    lg = net(xin)
+                loss = torch.mean(lm.bce_with_logits_elementwise(lg.float(), y, m.pos_weight.to(dev)) * w)
+                loss.backward()
+                opt.step()
+                return loss
+            for _ in range(warmup):
+                step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"tiles_per_s": B / (ms * 1e-3), "ms_per_step": ms}
+            del m, net, opt
+            torch.cuda.empty_cache()
+        except Exception as e:      # noqa: BLE001
+            out[name] = {"error": repr(e)[:200]}
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+    out["what"] = (f"PyTorch {torch.__version__} eager, restated smp.Unet(mobilenet_v2) + BCE + fused Adam, bs={B}, {S}x{S}x4, "
+                   f"inputs resident, {warmup} warm-up + {steps} timed steps (CUDA events)")
+    return out
+
+
+def mode_parity(dev, S):
+    """sigmoid-map / loss difference between the benchmarked bf16 tcgen05 mode and the fp32 parity mode (which
+    tests/test_gpu_parity512.py pins to the fp32 oracle at this tile size within 1e-4) on 2 tiles, train-mode BN."""
+    from starcop_b200 import synthetic
+    from starcop_b200.model_setup import get_model
+    from starcop_b200.settings import default_settings
+    b = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in synthetic.hyperstarcop_batch(2, size=S, seed=5).items()}
+    res = {}
+    for mode in ("f32", "bf16"):
+        torch.manual_seed(1234)
+        m = get_model(default_settings(pos_weight=1.0, compute_dtype=mode), None).to(dev).train()
+        with torch.no_grad():
+            lg = m(b["input"])
+            loss = m.training_step(b, 1)
+        res[mode] = (torch.sigmoid(lg), float(loss))
+        del m
+    d = (res["bf16"][0] - res["f32"][0]).abs()
+    return {"what": f"bf16 tcgen05 mode vs fp32 parity mode, 2 tiles {S}x{S}, train-mode BN, same weights",
+            "sigmoid_max_abs": d.max().item(), "sigmoid_mean_abs": d.mean().item(),
+            "loss_rel": abs(res["bf16"][1] - res["f32"][1]) / abs(res["f32"][1]),
+            "fp32_mode_vs_oracle": "<= 1e-4 sigmoid max-abs, 1e-5 loss (tests/test_gpu_parity512.py)"}
+
+
+def step_roofline(model, batch, pk):
+    """One eager train step with every kernel launch timed by CUDA events (starcop_b200/profiler.py; weight
+    gradients on the main stream for this pass): per-kernel-family table, the time-dominant kernel, and the
+    time-weighted aggregates for the whole step and for the convolution stack."""
+    from starcop_b200 import profiler
+    eng = model.network._engine
+    side = eng.side_wgrad
+    eng.side_wgrad = False
+    try:
+        model.train_step_fused(batch)                      # warm
+        with profiler.StepProfile() as prof:
+            model.train_step_fused(batch)
+    finally:
+        eng.side_wgrad = side
+    tab = prof.table(pk["bf16_tflops_sustained"], pk["hbm_gbs"])
+    tot_s = sum(f["s"] for f in tab.values())
+    agg = lambda names: (sum(tab[n]["roof_s"] for n in names if n in tab), sum(tab[n]["s"] for n in names if n in tab))
+    r_all, s_all = agg(tab.keys())
+    r_conv, s_conv = agg(profiler.CONV_STACK)
+    r_tc, s_tc = agg(profiler.TENSOR_KERNELS)
+    fl_tc = sum(tab[n]["flop"] for n in profiler.TENSOR_KERNELS if n in tab)
+    dom = max(tab, key=lambda n: tab[n]["s"])
+    d = tab[dom]
+    tensor_bound = d["flop"] / (pk["bf16_tflops_sustained"] * 1e12) > d["bytes"] / (pk["hbm_gbs"] * 1e9)
+    roof = {"kernel": dom, "launches_per_step": d["launches"], "share_of_step_kernel_time": d["s"] / tot_s,
+            "us_per_launch": d["s"] / d["launches"] * 1e6, "how": "CUDA events around every launch of one eager step, in-step cache state"}
+    if tensor_bound:
+        roof.update({"bound": "tensor", "achieved": d["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": d["tflops"] / pk["bf16_tflops_sustained"], "flop_per_launch": d["flop"] / d["launches"]})
+    else:
+        roof.update({"bound": "hbm", "achieved": d["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": d["gbs"] / pk["hbm_gbs"], "algorithmic_bytes_per_launch": d["bytes"] / d["launches"]})
+    roof["traffic"] = None
+    roof["peak_source"] = "MEASURED_PEAKS.json (sustained bf16 / HBM copy): kernel timed inside a long step"
+    table = {n: {"launches": f["launches"], "us": round(f["s"] * 1e6, 1), "share": round(f["s"] / tot_s, 4),
+                 "tflops": None if not f["flop"] else round(f["tflops"], 1), "gbs": round(f["gbs"], 1),
+                 "frac_of_roofline": round(f["frac_of_roofline"], 3)}
+             for n, f in sorted(tab.items(), key=lambda kv: -kv[1]["s"])}
+    summary = {"sum_kernel_us": round(tot_s * 1e6, 1),
+               "step_frac_of_roofline": r_all / s_all,
+               "conv_stack_frac_of_roofline": r_conv / s_conv if s_conv else None,
+               "conv_stack_share_of_step": s_conv / s_all,
+               "tensor_kernels_tflops": fl_tc / s_tc / 1e12 if s_tc else None,
+               "tensor_kernels_frac_of_sustained_peak": fl_tc / s_tc / 1e12 / pk["bf16_tflops_sustained"] if s_tc else None,
+               "tensor_kernels_frac_of_their_roofline": r_tc / s_tc if s_tc else None,
+               "definition": "roofline time per launch = max(FLOP / sustained bf16 peak, algorithmic bytes / HBM peak); fraction = sum(roofline) / sum(measured)"}
+    return roof, table, summary
 
 
 def spectral_products_bench(dev, pk, tiles=8, size=512, bands=125, iters=5):
@@ -157,14 +288,19 @@ def spectral_products_bench(dev, pk, tiles=8, size=512, bands=125, iters=5):
 
 
 def run_reference(args, rank):
+    """--impl reference: the reference's own CPU path (oracle port of its PyTorch fp32 module; the reference itself
+    cannot be installed here) on all host threads, on this arm's config: `--batch` tiles of
+    size x size x 4 per step, EXACTLY `--warmup` untimed and `--steps` timed steps (mean step time)."""
     if rank != 0:
         return
-    rate, med, cores, sample = cpu_reference_step_rate(args.size, max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+    rate, mean_s, cores, sample = cpu_reference_step_rate(args.size, args.steps, args.warmup, tiles=args.batch, stat="mean")
     line = {"impl": "reference", "metric": "512x512 hyperspectral tiles/sec (train step)", "value": rate,
             "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": mean_s * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"HyperSTARCOP U-Net train step, {args.size}x{args.size}x4 tiles (CPU PyTorch fp32)"},
+            "config": {"workload": f"configs[1] on the host CPU: HyperSTARCOP U-Net fwd+bwd+Adam, {args.size}x{args.size}x(mag1c+RGB) "
+                                   f"tiles, bs={args.batch}, PyTorch fp32, BN train mode",
+                       "global_batch": args.batch, "tile": [args.size, args.size, 4]},
             "cpu_baseline": {"value": rate, "unit": "tiles/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -295,12 +431,17 @@ def main():
     e2e_val = tiles / (ms_e2e / 1e3)
     h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
 
-    roof = model.network.bench_dominant_kernel(B, S) if hasattr(model.network, "bench_dominant_kernel") else None
     pk, pk_kind = peaks()
-    if roof is not None:
-        roof["peak"] = pk["bf16_tflops"]
-        roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["peak_source"] = f"{pk_kind} burst bf16 (kernel timed alone)"
+    pk.setdefault("bf16_tflops_sustained", pk.get("bf16_tflops", 1400.0))
+    roof = table = summary = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        roof, table, summary = step_roofline(model, resident, pk)
+        roof["peak_source"] = f"{pk_kind}: " + roof["peak_source"]
+    probe = model.network.bench_dominant_kernel(B, S) if hasattr(model.network, "bench_dominant_kernel") else None
+    if probe is not None:
+        probe["peak"] = pk["bf16_tflops"]
+        probe["frac"] = probe["achieved"] / probe["peak"]
+        probe["peak_source"] = f"{pk_kind} burst bf16 (kernel timed alone, cold rotating buffers)"
 
     spectral = None
     if rank == 0 and world == 1 and not args.no_spectral:
@@ -308,6 +449,16 @@ def main():
             spectral = spectral_products_bench(dev, pk)
         except Exception as e:          # noqa: BLE001  (reported, never silently dropped)
             spectral = {"error": repr(e)}
+    eager = parity = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            parity = mode_parity(dev, S)
+        except Exception as e:          # noqa: BLE001
+            parity = {"error": repr(e)[:200]}
+    if rank == 0 and world == 1 and not args.no_eager_baseline:
+        del graphed
+        torch.cuda.empty_cache()
+        eager = gpu_eager_baseline(dev, B, S)
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -325,18 +476,30 @@ def main():
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "unet_tflops": value * UNET_TRAIN_GFLOP_PER_TILE / 1e3,
-            "roofline": roof, "cpu_baseline": cpu, "spectral_products": spectral,
+            "unet_frac_of_sustained_bf16_peak": value * UNET_TRAIN_GFLOP_PER_TILE / 1e3 / pk["bf16_tflops_sustained"],
+            "roofline": roof, "roofline_summary": summary, "roofline_table": table,
+            "largest_gemm_probe": probe,
+            "cpu_baseline": cpu, "gpu_eager_baseline": eager, "parity": parity, "spectral_products": spectral,
         }
         emit(line)
     if world > 1:
-        # The captured CUDA graphs hold NCCL work: destroying the communicator (or normal interpreter teardown)
-        # with them alive was observed to hang forever AFTER the result line was printed.  Quiesce, agree that
-        # every rank is done, flush, and leave without running the NCCL / graph destructors.
+        # Orderly teardown: the captured CUDA graphs hold NCCL work, so they are destroyed BEFORE the communicator
+        # (destroying the process group under live graphs was observed to hang in round 1).  A watchdog ends the
+        # process if the teardown still stalls: the result line is already out, a hang must never eat the run.
+        import gc
         torch.cuda.synchronize()
         dist.barrier()
         sys.stdout.flush()
         sys.stderr.flush()
-        os._exit(0)
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        graphed = None
+        model = None
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        watchdog.cancel()
 
 
 if __name__ == "__main__":

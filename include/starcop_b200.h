@@ -61,8 +61,11 @@ int sc_normalize_pack(const float* x, const double* off, const double* fac, cons
 int sc_conv_fprop(const void* x, int ldx, const float* w_packed, const float* bias, void* y, int ldy,
                   int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                   int dtype, int accumulate, void* stream);
-/* dW[co,ci,kh,kw] (OIHW f32, torch layout) += sum_p x[p*stride-pad+k][ci] * dy[p][co]; caller zeroes dW */
-int sc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw,
+/* dW[co,ci,kh,kw] (OIHW f32, torch layout) += sum_p x[p*stride-pad+k][ci] * dy[p][co]; caller zeroes dW.
+ * Deterministic: the pixel splits write private partial gradients into `workspace`
+ * (sc_conv_wgrad_workspace_bytes bytes, may be NULL when that is 0) and are summed in split order. */
+int64_t sc_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+int sc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, float* workspace,
                   int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                   int dtype, void* stream);
 /* OIHW f32 -> packed [KH*KW][Cin][Cout] f32; flip_transpose != 0 builds the data-gradient filter
@@ -126,8 +129,9 @@ int sc_add_into(const void* a, int lda, int pooled, void* out, int ldo, int accu
 /* segmentation head Conv2d(16->1, k3, pad1, bias) (smp SegmentationHead) -- bandwidth bound, no MMA */
 int sc_head_fprop(const void* x, int ldx, const float* w, const float* bias, float* logits,
                   int N, int H, int W, int C, int dtype, void* stream);
+/* data gradient of the head (the weight / bias gradient is sc_head_wgrad_tiled) */
 int sc_head_bwd(const void* x, int ldx, const float* w, const float* dlogits, void* dx, int lddx,
-                float* dw, float* dbias, int N, int H, int W, int C, int dtype, void* stream);
+                int N, int H, int W, int C, int dtype, void* stream);
 
 /* the head's weight / bias gradient through the depthwise tile machinery (TMA halo-tile ring, per-CTA partial
  * rows: deterministic, no global atomics); dw / dbias are ACCUMULATED.  C in {8,16,24,32,48,64}. */
@@ -138,12 +142,16 @@ int sc_head_wgrad_tiled(const void* x, int ldx, const float* dlogits, float* dw,
 /* ---- A3/A4/A6: weighted BCE + decisions + confusion counts in ONE pass ----------------------
  * (model_module.py:76-79 train, :115-135 val, :191-212 batch_with_preds; torchmetrics
  * ConfusionMatrix.update).  logits/y/w: n = B*HW f32 (w may be NULL = no weight_loss).
- * loss_sum[0] += sum l*w (fp64).  Optional outputs (NULL to skip):
+ * loss_sum: NULL, or sc_bce_loss_words(B, HW) doubles: [0] += sum l*w (fp64), [1] a ticket word that must be
+ * zero on entry and is zero again on exit, [2...] per-block partial sums (scratch).  The total is formed in
+ * block order by the last block to finish: bit-identical from run to run (no floating-point atomics).
+ * Optional outputs (NULL to skip):
  *   grad        d mean(l*w)/d logits * grad_scale            (ATen's backward form)
  *   cm          int64[4] += [[TN,FP],[FN,TP]] for pred = logits >= 0      (val_step, :124)
  *   pred_count  int64[B] += per-tile sum of that pred                     (pred_classification)
  *   cm_sig / pred_count_sig: the same for pred = sigmoid(logits) > .5     (batch_with_preds :204)
  *   prediction, loss_px, loss_px_w (f32), pred_binary, differences (int64) per pixel. */
+int64_t sc_bce_loss_words(int B, int64_t HW);
 int sc_bce_fused(const float* logits, const float* y, const float* w, float pos_weight,
                  int B, int64_t HW, float grad_scale, double* loss_sum, float* grad,
                  int64_t* cm, int64_t* pred_count, int64_t* cm_sig, int64_t* pred_count_sig,
@@ -227,7 +235,11 @@ int sc_tc_pack_weights_batch(const sc_tc_pack_desc* descs_dev, int n, int64_t to
 int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void* y, int ldy, double* stats,
                      int* stats_rows_host, int N, int H, int W, int Cin, int Cout, int KH, int KW,
                      int stride, int accumulate, void* stream);
-int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw,
+/* dW (OIHW f32) += X^T dY.  The pixel range is split across CTAs; every split stores its partial tile into
+ * `partials` (sc_tc_conv_wgrad_workspace_bytes bytes; may be NULL when that is 0) and a second kernel sums the
+ * splits in order: no floating-point atomics, bit-identical from run to run. */
+int64_t sc_tc_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
+int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, float* partials,
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, void* stream);
 
 /* Thin-layer variant for 3x3 / stride 1 / pad 1 (decoder blocks 2-4, fprop and dgrad): the 18x10 input halo

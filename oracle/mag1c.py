@@ -23,7 +23,7 @@ def get_mask_bad_bands(wave):
 def band_keep_aviris(wavelengths):
     """process_aviris.py:192-195: not water vapour, 2122..2488 nm; must be one contiguous slice (:203-206)."""
     wavelengths = np.asarray(wavelengths)
-    keep = get_mask_bad_bands(wavelengths) & (wavelengths > 2122) & (wavelengths < 2488)
+    keep = get_mask_bad_bands(wavelengths) & (wavelengths >= 2122) & (wavelengths <= 2488)   # bounds are kept (:194-195)
     idx = np.where(keep)[0]
     assert len(idx) and np.all(np.diff(idx) == 1), "band selection must be contiguous"
     return slice(int(idx[0]), int(idx[-1]) + 1)

@@ -7,7 +7,7 @@ achieved TFLOP/s and the bf16 activation GB/s each launch moves (min traffic: in
 import argparse, ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from starcop_b200 import _lib
+from starcop_b200 import _lib, ops
 from starcop_b200._lib import call
 
 ap = argparse.ArgumentParser()
@@ -60,13 +60,14 @@ for name, cin, cout, k, div in layers:
     n = ctypes.c_int(0)
     flops = 2.0 * B * Ho * Wo * k * k * cin * cout
     byts = 2.0 * B * (H * W * cin + Ho * Wo * cout)
-    ops = {
+    ws = [None]
+    ops_ = {
         "fprop": lambda i: call("sc_tc_conv_fprop", xs[i % NB].data_ptr(), ldx, wb.data_ptr(), ys[i % NB].data_ptr(), cout,
                                 part.data_ptr(), ctypes.byref(n), B, H, W, cin, cout, k, k, stride, 0, st),
         "dgrad": lambda i: call("sc_tc_conv_fprop", ys[i % NB].data_ptr(), cout, wt.data_ptr(), xs[i % NB].data_ptr(), ldx,
                                 0, 0, B, Ho, Wo, cout, cin, k, k, 1, 0, st),
-        "wgrad": lambda i: call("sc_tc_conv_wgrad", xs[i % NB].data_ptr(), ldx, ys[i % NB].data_ptr(), cout, dw.data_ptr(),
-                                B, H, W, cin, cout, k, k, stride, st),
+        "wgrad": lambda i: ws.__setitem__(0, ops.tc_conv_wgrad(xs[i % NB], ldx, ys[i % NB], cout, dw, B, H, W, cin, cout, k,
+                                                               stride, workspace=ws[0])),
     }
     halo = k == 3 and stride == 1 and lib.sc_tc_halo_supported(cin, cout) and lib.sc_tc_halo_supported(cout, cin)
     if halo:
@@ -75,13 +76,13 @@ for name, cin, cout, k, div in layers:
         call("sc_tc_pack_weights", w.data_ptr(), wbh.data_ptr(), cout, cin, 3, 3, 0, hp, cout, st)
         wth = torch.empty(cin * 9 * hp2, dtype=torch.bfloat16, device=dev)
         call("sc_tc_pack_weights", w.data_ptr(), wth.data_ptr(), cout, cin, 3, 3, 1, cin, hp2, st)
-        ops["fprop_halo"] = lambda i: call("sc_tc_conv3x3_halo", xs[i % NB].data_ptr(), ldx, wbh.data_ptr(), ys[i % NB].data_ptr(),
+        ops_["fprop_halo"] = lambda i: call("sc_tc_conv3x3_halo", xs[i % NB].data_ptr(), ldx, wbh.data_ptr(), ys[i % NB].data_ptr(),
                                            cout, part.data_ptr(), ctypes.byref(n), B, H, W, cin, cout, 0, st)
-        ops["dgrad_halo"] = lambda i: call("sc_tc_conv3x3_halo", ys[i % NB].data_ptr(), cout, wth.data_ptr(), xs[i % NB].data_ptr(),
+        ops_["dgrad_halo"] = lambda i: call("sc_tc_conv3x3_halo", ys[i % NB].data_ptr(), cout, wth.data_ptr(), xs[i % NB].data_ptr(),
                                            ldx, 0, 0, B, H, W, cout, cin, 0, st)
     for op in a.ops.split(",") + (["fprop_halo", "dgrad_halo"] if halo else []):
         if op == "dgrad" and (stride != 1 or cin % 8): continue
-        us = timeit(ops[op])
+        us = timeit(ops_[op])
         tot[op] = tot.get(op, 0) + us
         print(f"{name:8s} {op:6s} {us:9.1f} {flops / us / 1e6:9.1f} {byts / us / 1e3:8.0f}  {cin}->{cout} k{k} @{H}x{W}")
 print("totals (us):", {k: round(v) for k, v in tot.items()})

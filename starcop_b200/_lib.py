@@ -20,7 +20,8 @@ SIGNATURES = {
     "sc_last_cuda_error": [],
     "sc_normalize_pack": [P, P, P, P, P, I, I, I, I, I, P, I, I, P, P],
     "sc_conv_fprop": [P, I, P, P, P, I, I, I, I, I, I, I, I, I, I, I, I, P],
-    "sc_conv_wgrad": [P, I, P, I, P, I, I, I, I, I, I, I, I, I, I, P],
+    "sc_conv_wgrad_workspace_bytes": [I, I, I, I, I, I, I, I, I],
+    "sc_conv_wgrad": [P, I, P, I, P, P, I, I, I, I, I, I, I, I, I, I, P],
     "sc_pack_weights": [P, P, I, I, I, I, I, P],
     "sc_dwconv_fprop": [P, I, P, P, I, P, P, I, P, P, I, I, I, I, I, I, P],
     "sc_dwconv_dgrad": [P, I, P, P, I, I, I, I, I, I, I, P],
@@ -34,9 +35,10 @@ SIGNATURES = {
     "sc_bn_bwd_apply": [P, I, I, P, I, P, P, P, P, P, I, P, I, P, I, P, P, I, I, I, I, I, P],
     "sc_add_into": [P, I, I, P, I, I, I, I, I, I, I, P],
     "sc_head_fprop": [P, I, P, P, P, I, I, I, I, I, P],
-    "sc_head_bwd": [P, I, P, P, P, I, P, P, I, I, I, I, I, P],
+    "sc_head_bwd": [P, I, P, P, P, I, I, I, I, I, I, P],
     "sc_head_wgrad_workspace_bytes": [I],
     "sc_head_wgrad_tiled": [P, I, P, P, P, P, I, I, I, I, I, P],
+    "sc_bce_loss_words": [I, L],
     "sc_bce_fused": [P, P, P, F, I, L, F, P, P, P, P, P, P, P, P, P, P, P, P],
     "sc_adam_step": [P, P, P, P, L, F, F, F, F, I, F, P],
     "sc_adam_step_dev": [P, P, P, P, L, P, F, F, F, P, F, P],
@@ -58,10 +60,12 @@ SIGNATURES = {
     "sc_tc_halo_cin_pad": [I],
     "sc_tc_halo_supported": [I, I],
     "sc_tc_conv3x3_halo": [P, I, P, P, I, P, P, I, I, I, I, I, I, P],
-    "sc_tc_conv_wgrad": [P, I, P, I, P, I, I, I, I, I, I, I, I, P],
+    "sc_tc_conv_wgrad_workspace_bytes": [I, I, I, I, I, I, I, I],
+    "sc_tc_conv_wgrad": [P, I, P, I, P, P, I, I, I, I, I, I, I, I, P],
 }
 _RESTYPES = {"sc_last_cuda_error": ctypes.c_char_p, "sc_mag1c_smem_bytes": c_int64, "sc_bn_partials_bytes": c_int64, "sc_mlr_workspace_bytes": c_int64, "sc_dwconv_wgrad_workspace_bytes": c_int64, "sc_head_wgrad_workspace_bytes": c_int64,
-             "sc_ratio_workspace_bytes": c_int64}
+             "sc_ratio_workspace_bytes": c_int64, "sc_conv_wgrad_workspace_bytes": c_int64,
+             "sc_tc_conv_wgrad_workspace_bytes": c_int64, "sc_bce_loss_words": c_int64}
 
 _lib = None
 

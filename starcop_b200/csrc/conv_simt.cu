@@ -219,13 +219,14 @@ extern "C" int sc_conv_fprop(const void* x, int ldx, const float* w_packed, cons
 
 // ------------------------------------------------------------------------------------------------
 // dense conv wgrad: per tap, dW[ci][co] = sum_p x[p@tap][ci] * dy[p][co]; 64x64 tile, split over
-// pixels, fp32 atomics into the torch-layout (OIHW) gradient.
+// pixels.  Each pixel split writes its own OIHW-shaped partial gradient into the workspace and a
+// second kernel sums the splits in order (deterministic: no floating-point atomics).
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(256)
 conv_wgrad_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, int lddy, float* __restrict__ dw,
-                  int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int Ho, int Wo,
-                  int ci_tiles, int psplit) {
+                  float* __restrict__ partials, int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
+                  int pad, int Ho, int Wo, int ci_tiles, int psplit) {
   constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
   __shared__ float As[BK][BM + 4];   // [pixel][ci]
   __shared__ float Bs[BK][BN + 4];   // [pixel][co]
@@ -294,6 +295,8 @@ conv_wgrad_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, in
       for (int j = 0; j < TN; ++j) acc[i][j] += part[i][j];
   }
   const int KK = KH * KW;
+  // one split: this block is the only writer of its elements; several: split z owns copy z of the workspace
+  float* dst = psplit == 1 ? dw : partials + (int64_t)blockIdx.z * Cout * Cin * KK;
 #pragma unroll
   for (int i = 0; i < TM; ++i) {
     int ci = ci0 + ty * TM + i;
@@ -302,15 +305,22 @@ conv_wgrad_kernel(const T* __restrict__ x, int ldx, const T* __restrict__ dy, in
     for (int j = 0; j < TN; ++j) {
       int co = co0 + tx * TN + j;
       if (co >= Cout) continue;
-      atomicAdd(&dw[((int64_t)co * Cin + ci) * KK + tap], acc[i][j]);
+      const int64_t o = ((int64_t)co * Cin + ci) * KK + tap;
+      if (psplit == 1) dst[o] += acc[i][j];
+      else dst[o] = acc[i][j];
     }
   }
 }
 
-extern "C" int sc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, int N, int H, int W,
-                             int Cin, int Cout, int KH, int KW, int stride, int pad, int dtype, void* stream) {
-  if (!x || !dy || !dw_oihw || N <= 0) return SC_ERR_BAD_ARG;
-  int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+__global__ void conv_wgrad_sum_kernel(const float* __restrict__ partials, int psplit, int64_t n, float* __restrict__ dw) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = partials[i];
+    for (int z = 1; z < psplit; ++z) s += partials[(int64_t)z * n + i];     // fixed order
+    dw[i] += s;
+  }
+}
+
+static int simt_wgrad_split(int N, int Ho, int Wo, int Cin, int Cout, int KH, int KW) {
   int64_t P = (int64_t)N * Ho * Wo;
   int ci_tiles = ceil_div(Cin, 64), co_tiles = ceil_div(Cout, 64);
   int base = ci_tiles * KH * KW * co_tiles;
@@ -318,9 +328,34 @@ extern "C" int sc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, f
   int64_t max_split = (P + 255) / 256;
   if (psplit > max_split) psplit = (int)max_split;
   if (psplit < 1) psplit = 1;
+  // every split non-empty (chunks are multiples of 16 pixels)
+  const int64_t chunk = ((P + psplit - 1) / psplit + 15) / 16 * 16;
+  return (int)((P + chunk - 1) / chunk);
+}
+
+extern "C" int64_t sc_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
+  int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  int psplit = simt_wgrad_split(N, Ho, Wo, Cin, Cout, KH, KW);
+  return psplit > 1 ? (int64_t)psplit * Cout * Cin * KH * KW * sizeof(float) : 0;
+}
+
+extern "C" int sc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, float* workspace, int N,
+                             int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, int dtype, void* stream) {
+  if (!x || !dy || !dw_oihw || N <= 0) return SC_ERR_BAD_ARG;
+  int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  int ci_tiles = ceil_div(Cin, 64), co_tiles = ceil_div(Cout, 64);
+  const int psplit = simt_wgrad_split(N, Ho, Wo, Cin, Cout, KH, KW);
+  if (psplit > 1 && !workspace) return SC_ERR_BAD_ARG;
   dim3 grid(ci_tiles * KH * KW, co_tiles, psplit);
-  SC_DISPATCH_DTYPE(dtype, (conv_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
-                               (const T*)x, ldx, (const T*)dy, lddy, dw_oihw, N, H, W, Cin, Cout, KH, KW, stride,
-                               pad, Ho, Wo, ci_tiles, psplit)));
+  cudaStream_t st = (cudaStream_t)stream;
+  SC_DISPATCH_DTYPE(dtype, (conv_wgrad_kernel<T><<<grid, 256, 0, st>>>(
+                               (const T*)x, ldx, (const T*)dy, lddy, dw_oihw, workspace, N, H, W, Cin, Cout, KH, KW,
+                               stride, pad, Ho, Wo, ci_tiles, psplit)));
+  int rc = check_launch();
+  if (rc != SC_OK || psplit == 1) return rc;
+  const int64_t n = (int64_t)Cout * Cin * KH * KW;
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  conv_wgrad_sum_kernel<<<(int)blocks, 256, 0, st>>>(workspace, psplit, n, dw_oihw);
   return check_launch();
 }

@@ -9,8 +9,10 @@
 //   overlaps the MMAs of tile i+1.
 // wgrad:  dW[(tap,ci)][co] = sum_pixels X[pixel@tap][ci] * dY[pixel][co]; both operands are read in
 //   their natural NHWC layout as MN-major UMMA operands (the reduction runs over pixels), M = 128
-//   rows made of 128/KC shifted activation boxes, split over pixels across CTAs, fp32 atomics into
-//   the torch-layout gradient.
+//   rows made of 128/KC shifted activation boxes, split over pixels across CTAs.  Every split writes
+//   its 128 x block_n partial tile to a workspace; the LAST split of a tile to finish (a ticket counter)
+//   sums the partials in split order and adds the result into the torch-layout gradient: no floating
+//   point atomics, run-to-run bit-identical.
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -20,22 +22,7 @@ using namespace tc;
 // ------------------------------------------------------------------------------------------------
 // driver entry point for tensor-map encoding (no link-time libcuda dependency)
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
+static EncodeTiledFn get_encode() { return encode_tiled_fn(); }
 
 static CUtensorMapSwizzle swizzle_for(int row_bytes) {
   return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -190,6 +177,7 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);     // [2][Cout] per-CTA partial statistics
+  float* s_part = s_stats + 2 * p.Cout;                         // [4 warps][2][block_n] one tile's column sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -393,15 +381,30 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           }
           float s1 = v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
           float s2 = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
-          int ch = n0 + c0 + my_col;
-          if ((lane & 1) == 0 && ch < p.Cout) {
-            atomicAdd(&s_stats[ch], s1);
-            atomicAdd(&s_stats[p.Cout + ch], s2);
+          if ((lane & 1) == 0) {
+            s_part[q * 2 * p.block_n + c0 + my_col] = s1;
+            s_part[q * 2 * p.block_n + p.block_n + c0 + my_col] = s2;
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
+      if (p.stats) {
+        // the four warps' column sums are combined in a fixed order by the channel's owner thread (no
+        // shared-memory atomics: their arrival order would make the fp32 sums differ run to run)
+        asm volatile("bar.sync 1, 128;");
+        for (int c = et; c < p.block_n; c += 128) {
+          const int ch = n0 + c;
+          if (ch < p.Cout) {
+            const float* sp = s_part + c;
+            const int st = 2 * p.block_n;
+            s_stats[ch] += (sp[0] + sp[st]) + (sp[2 * st] + sp[3 * st]);
+            sp += p.block_n;
+            s_stats[p.Cout + ch] += (sp[0] + sp[st]) + (sp[2 * st] + sp[3 * st]);
+          }
+        }
+        asm volatile("bar.sync 1, 128;");
+      }
     }
     if (p.stats) {
       // one partial row per CTA (BatchNorm partial-sum protocol, see sc_bn_stats): no global atomics
@@ -463,7 +466,7 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
   if (groups < 1) groups = 1;
   p.groups = groups;
   const int stage_bytes = groups * group_bytes;
-  const int tail = 1024 + 256 + (stats ? 2 * Cout * 4 : 0);   // alignment slack + barriers + statistics
+  const int tail = 1024 + 256 + (stats ? (2 * Cout + 8 * p.block_n) * 4 : 0);   // alignment slack + barriers + statistics
   // Short-K layers (the 1x1 expansions / projections: one or two MMAs per tile) are bound by the per-tile
   // TMA -> MMA -> epilogue hand-offs, not by the tensor pipe: run TWO CTAs per SM (half the shared memory,
   // 256 TMEM columns each) so twice as many tiles are in flight.
@@ -489,13 +492,10 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_FPROP(KC)                                                                                     \
   do {                                                                                                       \
-    static bool attr_set = false; /* opt in once to the full dynamic shared memory (not a stream op) */      \
-    if (!attr_set) {                                                                                         \
-      cudaError_t e = cudaFuncSetAttribute(tc_conv_fprop_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           kMaxDynSmem);                                                     \
-      if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                        \
-      attr_set = true;                                                                                       \
-    }                                                                                                        \
+    /* opt in to the full dynamic shared memory: a per-device function attribute, not a stream operation */  \
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_fprop_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         kMaxDynSmem);                                                       \
+    if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                          \
     tc_conv_fprop_kernel<KC><<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);                                   \
   } while (0)
   if (kc == 64) LAUNCH_FPROP(64);
@@ -517,7 +517,45 @@ struct WgradParams {
   int cchunks, subs_total;         // sub-blocks (tap, channel chunk) of KC rows each
   int stages;
   float* dw;
+  float* partials;                 // [m_blocks * n_blocks][ksplit][128][block_n] fp32 (ksplit > 1)
 };
+
+// dW += sum over the pixel splits of their partial tiles, in split order (deterministic).  One thread per float4 of
+// a tile: coalesced reads of the (mostly L2-resident) partials, scattered adds into the OIHW gradient.
+template <int KC>
+__global__ void __launch_bounds__(256)
+tc_wgrad_reduce_kernel(WgradParams p) {
+  constexpr int SUBS = 128 / KC;
+  const int tile_elems = 128 * p.block_n;
+  const int bn4 = p.block_n / 4;
+  const int KK = p.KH * p.KW;
+  const int64_t total4 = (int64_t)p.m_blocks * p.n_blocks * (tile_elems / 4);
+  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total4; g += (int64_t)gridDim.x * blockDim.x) {
+    const int tile_id = (int)(g / (tile_elems / 4));
+    const int e = (int)(g - (int64_t)tile_id * (tile_elems / 4));
+    const int nb = tile_id / p.m_blocks, mb = tile_id - nb * p.m_blocks;
+    const int r = e / bn4, c = (e - r * bn4) * 4;
+    const int sidx = r / KC, cil = r % KC;
+    const int j = mb * SUBS + sidx;
+    if (j >= p.subs_total) continue;
+    const int tap = j / p.cchunks;
+    const int ci = (j - tap * p.cchunks) * KC + cil;
+    if (ci >= p.Cin) continue;
+    const float* base = p.partials + (size_t)tile_id * p.ksplit * tile_elems + (size_t)e * 4;
+    float4 a = __ldcg(reinterpret_cast<const float4*>(base));
+    for (int k = 1; k < p.ksplit; ++k) {
+      const float4 b = __ldcg(reinterpret_cast<const float4*>(base + (size_t)k * tile_elems));
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    const float av[4] = {a.x, a.y, a.z, a.w};
+    const int n0 = nb * p.block_n;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int co = n0 + c + i;
+      if (co < p.Cout) p.dw[((int64_t)co * p.Cin + ci) * KK + tap] += av[i];
+    }
+  }
+}
 
 template <int KC>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -641,29 +679,45 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       umma_commit(tfull);
     }
   } else {
+    // epilogue (every split holds >= 1 pixel tile: the host sizes ksplit that way)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    if (nsteps > 0) {
-      mbar_wait(tfull, 0);
-      tc_fence_after();
-      const int s = row / KC, cil = row % KC;
+    const int KK = p.KH * p.KW;
+    // OIHW offset of accumulator row r (tap, ci) of this M block, or -1 for a padding row
+    auto row_offset = [&](int r) -> int64_t {
+      const int s = r / KC, cil = r % KC;
+      if (s >= valid_subs) return -1;
       const int j = mb * SUBS + s;
-      bool row_ok = s < valid_subs;
-      const int tap = row_ok ? j / p.cchunks : 0;
-      const int ci = row_ok ? (j - tap * p.cchunks) * KC + cil : 0;
-      row_ok = row_ok && ci < p.Cin;
-      const int KK = p.KH * p.KW;
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+      const int tap = j / p.cchunks;
+      const int ci = (j - tap * p.cchunks) * KC + cil;
+      return ci < p.Cin ? (int64_t)ci * KK + tap : -1;
+    };
+    mbar_wait(tfull, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (p.ksplit == 1) {
+      const int64_t ro = row_offset(row);
       for (int c0 = 0; c0 < p.block_n; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);
-        if (row_ok) {
+        if (ro >= 0) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            int co = n0 + c0 + i;
-            if (co < p.Cout) atomicAdd(&p.dw[((int64_t)co * p.Cin + ci) * KK + tap], v[i]);
+            const int co = n0 + c0 + i;
+            if (co < p.Cout) p.dw[(int64_t)co * p.Cin * KK + ro] += v[i];     // this CTA is the element's only writer
           }
         }
+      }
+    } else {
+      // this split's partial tile; tc_wgrad_reduce_kernel sums the splits in order
+      const int tile_id = nb * p.m_blocks + mb;
+      const int tile_elems = 128 * p.block_n;
+      float* mine = p.partials + ((size_t)tile_id * p.ksplit + ks) * tile_elems + (size_t)row * p.block_n;
+      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+        float v[16];
+        tmem_ld16(taddr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(mine + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
       }
     }
   }
@@ -675,36 +729,58 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
-extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, int N, int H, int W,
-                                int Cin, int Cout, int KH, int KW, int stride, void* stream) {
+// geometry shared by the launcher and the workspace query
+static int wgrad_geometry(int N, int Ho, int Wo, int Cin, int Cout, int KH, int KW, WgradParams* p, int* kc_out) {
+  const int kc = pick_kc(Cin);
+  p->tiles_w = Wo / 16; p->tiles_h = Ho / 4;
+  p->p_tiles = N * p->tiles_w * p->tiles_h;
+  p->kcb = pick_kc(Cout);
+  int nt = (Cout + 255) / 256;
+  p->block_n = ((Cout + nt - 1) / nt + p->kcb - 1) / p->kcb * p->kcb;
+  if (p->block_n > 256) return SC_ERR_UNSUPPORTED;
+  p->n_blocks = (Cout + p->block_n - 1) / p->block_n;
+  p->nb_boxes = p->block_n / p->kcb;
+  p->cchunks = (Cin + kc - 1) / kc;
+  p->subs_total = KH * KW * p->cchunks;
+  const int subs = 128 / kc;
+  p->m_blocks = (p->subs_total + subs - 1) / subs;
+  int base = p->m_blocks * p->n_blocks;
+  int ksplit = (kNumSMs * 2 + base - 1) / base;
+  int max_split = (p->p_tiles + 7) / 8;                    // >= 8 pixel tiles (512 px) per CTA
+  if (ksplit > max_split) ksplit = max_split;
+  if (ksplit < 1) ksplit = 1;
+  // every split must own at least one pixel tile (its partial tile enters the ordered sum)
+  const int per = (p->p_tiles + ksplit - 1) / ksplit;
+  p->ksplit = (p->p_tiles + per - 1) / per;
+  *kc_out = kc;
+  return SC_OK;
+}
+
+extern "C" int64_t sc_tc_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
+  const int Ho = stride == 1 ? H : (H + 2 * (KH / 2) - KH) / 2 + 1;
+  const int Wo = stride == 1 ? W : (W + 2 * (KW / 2) - KW) / 2 + 1;
+  WgradParams p;
+  int kc;
+  if (Cin < 1 || wgrad_geometry(N, Ho, Wo, Cin, Cout, KH, KW, &p, &kc) != SC_OK) return -1;
+  return p.ksplit > 1 ? (int64_t)p.m_blocks * p.n_blocks * p.ksplit * 128 * p.block_n * sizeof(float) : 0;
+}
+
+extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, float* partials,
+                                int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, void* stream) {
   if (!x || !dy || !dw_oihw) return SC_ERR_BAD_ARG;
   if (stride != 1 && stride != 2) return SC_ERR_UNSUPPORTED;
   const int Ho = stride == 1 ? H : (H + 2 * (KH / 2) - KH) / 2 + 1;
   const int Wo = stride == 1 ? W : (W + 2 * (KW / 2) - KW) / 2 + 1;
   if (Cin < 1 || Cout % 8 || Wo % 16 || Ho % 4 || ldx % 8 || lddy % 8 || KH != KW || (KH != 1 && KH != 3))
     return SC_ERR_UNSUPPORTED;
-  const int kc = pick_kc(Cin);
   WgradParams p;
+  int kc;
   p.N = N; p.H = Ho; p.W = Wo; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.stride = stride;
-  p.tiles_w = Wo / 16; p.tiles_h = Ho / 4;
-  p.p_tiles = N * p.tiles_w * p.tiles_h;
-  p.kcb = pick_kc(Cout);
-  int nt = (Cout + 255) / 256;
-  p.block_n = ((Cout + nt - 1) / nt + p.kcb - 1) / p.kcb * p.kcb;
-  if (p.block_n > 256) return SC_ERR_UNSUPPORTED;
-  p.n_blocks = (Cout + p.block_n - 1) / p.block_n;
-  p.nb_boxes = p.block_n / p.kcb;
-  p.cchunks = (Cin + kc - 1) / kc;
-  p.subs_total = KH * KW * p.cchunks;
-  const int subs = 128 / kc;
-  p.m_blocks = (p.subs_total + subs - 1) / subs;
-  int base = p.m_blocks * p.n_blocks;
-  int ksplit = (kNumSMs * 2 + base - 1) / base;
-  int max_split = (p.p_tiles + 7) / 8;                    // >= 8 pixel tiles (512 px) per CTA
-  if (ksplit > max_split) ksplit = max_split;
-  if (ksplit < 1) ksplit = 1;
-  p.ksplit = ksplit;
+  int rc = wgrad_geometry(N, Ho, Wo, Cin, Cout, KH, KW, &p, &kc);
+  if (rc != SC_OK) return rc;
+  if (p.ksplit > 1 && !partials) return SC_ERR_BAD_ARG;
   p.dw = dw_oihw;
+  p.partials = partials;
   const int stage_bytes = (64 * 128 * 2 + p.nb_boxes * 64 * p.kcb * 2 + 1023) & ~1023;
   const int tail = 1024 + 256;
   int stages = (200 * 1024 - tail) / stage_bytes;
@@ -714,7 +790,7 @@ extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy
   const size_t smem = (size_t)stages * stage_bytes + tail;
 
   CUtensorMap tmX, tmDY;
-  int rc = encode_act(&tmX, x, Cin, W, H, N, ldx, kc, 16, 4, stride);
+  rc = encode_act(&tmX, x, Cin, W, H, N, ldx, kc, 16, 4, stride);
   if (rc != SC_OK) return rc;
   rc = encode_act(&tmDY, dy, Cout, Wo, Ho, N, lddy, p.kcb, 16, 4);
   if (rc != SC_OK) return rc;
@@ -722,14 +798,16 @@ extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy
   cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_WGRAD(KC)                                                                                     \
   do {                                                                                                       \
-    static bool attr_set = false;                                                                            \
-    if (!attr_set) {                                                                                         \
-      cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           kMaxDynSmem);                                                     \
-      if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                        \
-      attr_set = true;                                                                                       \
-    }                                                                                                        \
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         kMaxDynSmem);                                                       \
+    if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                          \
     tc_conv_wgrad_kernel<KC><<<grid, kTcThreads, smem, st>>>(tmX, tmDY, p);                                  \
+    if (p.ksplit > 1) {                                                                                      \
+      const int64_t total4 = (int64_t)p.m_blocks * p.n_blocks * 32 * p.block_n;                              \
+      int64_t rb = (total4 + 255) / 256;                                                                     \
+      if (rb > kNumSMs * 8) rb = kNumSMs * 8;                                                                \
+      tc_wgrad_reduce_kernel<KC><<<(int)rb, 256, 0, st>>>(p);                                                \
+    }                                                                                                        \
   } while (0)
   if (kc == 64) LAUNCH_WGRAD(64);
   else if (kc == 32) LAUNCH_WGRAD(32);

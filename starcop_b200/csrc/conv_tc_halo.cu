@@ -79,7 +79,8 @@ tc_conv3x3_halo_kernel(HaloParams p) {
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);         // [2][Cout]
-  int2* tab = reinterpret_cast<int2*>(s_stats + 2 * p.Cout);        // [np*180] granule map (8 B aligned: Cout % 16 == 0)
+  float* s_part = s_stats + 2 * p.Cout;                             // [4 warps][2][Cout] one batch's column sums
+  int2* tab = reinterpret_cast<int2*>(s_part + 8 * p.Cout);         // [np*180] granule map (8 B aligned: Cout % 16 == 0)
   const int ngran = np * kPatchH * kPatchW;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -333,15 +334,24 @@ tc_conv3x3_halo_kernel(HaloParams p) {
           }
           const float s1 = sv[0] + __shfl_xor_sync(0xffffffffu, sv[0], 1);
           const float s2 = sq[0] + __shfl_xor_sync(0xffffffffu, sq[0], 1);
-          const int ch = c0 + my_col;
           if ((lane & 1) == 0) {
-            atomicAdd(&s_stats[ch], s1);
-            atomicAdd(&s_stats[p.Cout + ch], s2);
+            s_part[q * 2 * p.Cout + c0 + my_col] = s1;
+            s_part[q * 2 * p.Cout + p.Cout + c0 + my_col] = s2;
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
+      if (p.stats) {
+        // fixed-order combination of the four warps' column sums by the channel's owner thread (deterministic)
+        asm volatile("bar.sync 1, 128;");
+        for (int c = et; c < 2 * p.Cout; c += 128) {
+          const float* sp = s_part + c;
+          const int st = 2 * p.Cout;
+          s_stats[c] += (sp[0] + sp[st]) + (sp[2 * st] + sp[3 * st]);
+        }
+        asm volatile("bar.sync 1, 128;");
+      }
     }
     if (p.stats) {
       // one partial row per CTA (BatchNorm partial-sum protocol, see sc_bn_stats): no global atomics
@@ -360,7 +370,7 @@ tc_conv3x3_halo_kernel(HaloParams p) {
 
 static size_t halo_smem(int np, int Cout, int stages, bool stats) {
   const size_t b = ((size_t)9 * np * Cout * 16 + 127) & ~(size_t)127;
-  return b + (size_t)stages * np * kPlaneStride + (size_t)(2 * stages + 4) * 8 + 16 + 2 * Cout * 4 + (size_t)np * kPatchH * kPatchW * 8 + 64;
+  return b + (size_t)stages * np * kPlaneStride + (size_t)(2 * stages + 4) * 8 + 16 + 10 * Cout * 4 + (size_t)np * kPatchH * kPatchW * 8 + 64;
 }
 
 }  // namespace
@@ -424,14 +434,12 @@ extern "C" int sc_tc_conv3x3_halo(const void* x, int ldx, const void* w_bf16, vo
   if ((int64_t)(kPatchH * W + kPatchW) * ldx + Cin > INT32_MAX) return SC_ERR_BAD_ARG;
   const int grid = p.m_tiles < kNumSMs * best_ctas ? p.m_tiles : kNumSMs * best_ctas;
   if (stats) *stats_rows_host = grid;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {
     cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem - 1024);
     if (e != cudaSuccess) {
       g_last_error = e;
       return SC_ERR_CUDA;
     }
-    attr_set = true;
   }
   tc_conv3x3_halo_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   return check_launch();

@@ -752,84 +752,12 @@ __global__ void head_dgrad_kernel(const float* __restrict__ w, const float* __re
   }
 }
 
-template <typename T>
-__global__ void head_wgrad_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ dl,
-                                  float* __restrict__ dw, float* __restrict__ dbias, int N, int H, int W, int C) {
-  // thread = (pixel lane, 8-channel vector); 72 fp32 partials per thread, block-reduced in smem
-  __shared__ float sm[9 * kHeadMaxC + 1];
-  int CV = C / 8, PL = blockDim.x / CV;
-  int cv = threadIdx.x % CV, pl = threadIdx.x / CV;
-  for (int i = threadIdx.x; i < 9 * C + 1; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  float acc[9][8];
-  float bsum = 0.f;
-#pragma unroll
-  for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[tp][i] = 0.f;
-  int64_t total = (int64_t)N * H * W;
-  if (pl < PL) {
-    for (int64_t p = (int64_t)blockIdx.x * PL + pl; p < total; p += (int64_t)gridDim.x * PL) {
-      int wq = (int)(p % W);
-      int64_t t = p / W;
-      int h = (int)(t % H);
-      float g = dl[p];
-      if (cv == 0) bsum += g;
-#pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        int ih = h + kh - 1;
-        if (ih < 0 || ih >= H) continue;
-#pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          int iw = wq + kw - 1;
-          if (iw < 0 || iw >= W) continue;
-          f8 v = load8<T>(x + (p + (int64_t)(kh - 1) * W + (kw - 1)) * ldx + cv * 8);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[kh * 3 + kw][i] = fmaf(v.v[i], g, acc[kh * 3 + kw][i]);
-        }
-      }
-    }
-  }
-  // lanes with equal (lane % CV) own the same channels (32 % CV == 0): butterfly over the others
-  const int lane = threadIdx.x & 31;
-  for (int m = CV; m < 32; m <<= 1) {
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[tp][i] += __shfl_xor_sync(0xffffffffu, acc[tp][i], m);
-    bsum += __shfl_xor_sync(0xffffffffu, bsum, m);
-  }
-  if (lane < CV) {
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(&sm[tp * C + lane * 8 + i], acc[tp][i]);
-    if (lane == 0) atomicAdd(&sm[9 * C], bsum);
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
-    int tap = i / C, c = i % C;
-    atomicAdd(&dw[c * 9 + tap], sm[i]);
-  }
-  if (threadIdx.x == 0 && dbias) atomicAdd(dbias, sm[9 * C]);
-}
-
 extern "C" int sc_head_bwd(const void* x, int ldx, const float* w, const float* dlogits, void* dx, int lddx,
-                           float* dw, float* dbias, int N, int H, int W, int C, int dtype, void* stream) {
-  if (!x || !w || !dlogits || C % 8 || C > kHeadMaxC || ldx % 8 || 32 % (C / 8)) return SC_ERR_BAD_ARG;
+                           int N, int H, int W, int C, int dtype, void* stream) {
+  if (!x || !w || !dlogits || !dx || C % 8 || C > kHeadMaxC || ldx % 8 || lddx % 8) return SC_ERR_BAD_ARG;
   int64_t total = (int64_t)N * H * W;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dx) {
-    if (lddx % 8) return SC_ERR_BAD_ARG;
-    SC_DISPATCH_DTYPE(dtype, (head_dgrad_kernel<T><<<ew_blocks(total), 256, 0, st>>>(w, dlogits, (T*)dx, lddx, N, H, W, C)));
-  }
-  if (dw) {
-    int PL = 256 / (C / 8);
-    int blocks = (int)((total + PL * 16 - 1) / (PL * 16));
-    if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-    if (blocks < 1) blocks = 1;
-    SC_DISPATCH_DTYPE(dtype, (head_wgrad_kernel<T><<<blocks, 256, 0, st>>>((const T*)x, ldx, dlogits, dw, dbias, N, H, W, C)));
-  }
+  SC_DISPATCH_DTYPE(dtype, (head_dgrad_kernel<T><<<ew_blocks(total), 256, 0, st>>>(w, dlogits, (T*)dx, lddx, N, H, W, C)));
   return check_launch();
 }
 
@@ -872,9 +800,9 @@ __global__ void bce_fused_kernel(const float* __restrict__ logits, const float* 
     if (pred_binary) pred_binary[i] = ps;
     if (differences) differences[i] = 2 * ps + (t == 1.f ? 1 : 0);   // model_module.py:268-269
   }
-  __shared__ double s_l;
+  __shared__ double s_l[8];
   __shared__ long long s_c[8];
-  if (threadIdx.x == 0) s_l = 0.0;
+  __shared__ unsigned int s_last;
   if (threadIdx.x < 8) s_c[threadIdx.x] = 0;
   __syncthreads();
   lsum = warp_sum(lsum);
@@ -884,16 +812,15 @@ __global__ void bce_fused_kernel(const float* __restrict__ logits, const float* 
     c_sig[k] = warp_sum(c_sig[k]);
   }
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&s_l, lsum);
+    s_l[threadIdx.x >> 5] = lsum;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      atomicAdd((unsigned long long*)&s_c[k], (unsigned long long)c_val[k]);
+      atomicAdd((unsigned long long*)&s_c[k], (unsigned long long)c_val[k]);        // integers: exact in any order
       atomicAdd((unsigned long long*)&s_c[4 + k], (unsigned long long)c_sig[k]);
     }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (loss_sum) atomicAdd(loss_sum, s_l);
     if (cm)
       for (int k = 0; k < 4; ++k) atomicAdd((unsigned long long*)&cm[k], (unsigned long long)s_c[k]);
     if (cm_sig)
@@ -901,6 +828,47 @@ __global__ void bce_fused_kernel(const float* __restrict__ logits, const float* 
     if (pred_count) atomicAdd((unsigned long long*)&pred_count[b], (unsigned long long)(s_c[1] + s_c[3]));
     if (pred_count_sig) atomicAdd((unsigned long long*)&pred_count_sig[b], (unsigned long long)(s_c[5] + s_c[7]));
   }
+  if (!loss_sum) return;
+  // The loss is a floating-point sum: every block publishes its partial, and the LAST block to finish (ticket in
+  // loss_sum[1]) adds them up in block order -- the result does not depend on the blocks' arrival order.
+  const unsigned int nblocks = gridDim.x * gridDim.y;
+  const unsigned int bid = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += s_l[k];
+    loss_sum[2 + bid] = t;
+    __threadfence();
+    const unsigned long long tk = atomicAdd(reinterpret_cast<unsigned long long*>(loss_sum + 1), 1ull);
+    s_last = (tk == nblocks - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  __shared__ double s_red[256];
+  double t = 0.0;
+  for (unsigned int k = threadIdx.x; k < nblocks; k += blockDim.x) t += __ldcg(loss_sum + 2 + k);
+  s_red[threadIdx.x] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < (int)blockDim.x; ++k) tot += s_red[k];
+    loss_sum[0] += tot;
+    *reinterpret_cast<unsigned long long*>(loss_sum + 1) = 0ull;     // ticket ready for the next launch
+  }
+}
+
+static dim3 bce_grid(int B, int64_t HW) {
+  int bx = (int)((HW + 1023) / 1024);
+  int cap = (kNumSMs * 8 + B - 1) / B;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return dim3(bx, B);
+}
+
+extern "C" int64_t sc_bce_loss_words(int B, int64_t HW) {
+  if (B <= 0 || HW <= 0) return -1;
+  const dim3 g = bce_grid(B, HW);
+  return 2 + (int64_t)g.x * g.y;
 }
 
 extern "C" int sc_bce_fused(const float* logits, const float* y, const float* w, float pos_weight, int B,
@@ -908,13 +876,8 @@ extern "C" int sc_bce_fused(const float* logits, const float* y, const float* w,
                             int64_t* pred_count, int64_t* cm_sig, int64_t* pred_count_sig, float* prediction,
                             float* loss_px, float* loss_px_w, int64_t* pred_binary, int64_t* differences,
                             void* stream) {
-  if (!logits || !y || B <= 0 || HW <= 0) return SC_ERR_BAD_ARG;
-  int bx = (int)((HW + 1023) / 1024);
-  int cap = (kNumSMs * 8 + B - 1) / B;
-  if (bx > cap) bx = cap;
-  if (bx < 1) bx = 1;
-  dim3 grid(bx, B);
-  bce_fused_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+  if (!logits || !y || B <= 0 || HW <= 0 || B > 65535) return SC_ERR_BAD_ARG;
+  bce_fused_kernel<<<bce_grid(B, HW), 256, 0, (cudaStream_t)stream>>>(
       logits, y, w, pos_weight, HW, grad_scale, loss_sum, grad, (long long*)cm, (long long*)pred_count,
       (long long*)cm_sig, (long long*)pred_count_sig, prediction, loss_px, loss_px_w, (long long*)pred_binary,
       (long long*)differences);

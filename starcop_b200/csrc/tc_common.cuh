@@ -150,16 +150,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 inline EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  // C++11 function-local static: initialised exactly once, thread-safe
+  static const EncodeTiledFn fn = []() -> EncodeTiledFn {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
         q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
+      return (EncodeTiledFn)p;
+    return nullptr;
+  }();
   return fn;
 }
 // NHWC activation tensor (C, W, H, N), channel stride ld elements of esize bytes (2: bf16, 4: f32);

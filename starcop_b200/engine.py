@@ -50,6 +50,7 @@ class Arena:
         self.chunks = []          # (tensor, base, size)
         self.cur = 0
         self.off = 0
+        self.zeroed = 0           # chunks cleared since the last reset (zero-initialised arenas only)
 
     def reset(self):
         self.cur, self.off = 0, 0
@@ -97,24 +98,39 @@ class UNetEngine:
         self.stream = 0
         self.use_tc = self.dtype == SC_BF16 and bool(_lib.load().sc_tc_supported())
         self.use_halo = os.environ.get("STARCOP_NO_HALO", "") == ""
+        # weight gradients leave the critical path: they only feed the optimiser, so every wgrad kernel is issued on a
+        # side stream (forked from / joined to the main stream with events, inside a CUDA graph these are just
+        # edges) and overlaps the data-gradient / BatchNorm chain.  Results are unchanged: each gradient tensor has
+        # one writer, and the arenas never reuse a buffer within a step.
+        self.side_wgrad = os.environ.get("STARCOP_NO_SIDE_STREAM", "") == ""
+        self._side = None
+        self._main_obj = None
+        self._arenas = {}                # "train" / "eval" -> (activation arena, zero-initialised arena)
+        self.generation = 0              # bumped by every recording forward; a backward must match it
+        self._tape_generation = -1
         self._packs = {}                 # (weight name, flip) -> (bf16 buffer, descriptor fields), insertion ordered
         self._pack_table = None
         self._packed_this_step = False
         self._plan_complete = False      # set once a full forward + backward has recorded every request
 
     # ------------------------------------------------------------------ memory
-    def begin_step(self):
-        """Reset the bump allocators; the zero-initialised region (BN / reduction accumulators) is
-        cleared with ONE memset per chunk instead of one per buffer."""
-        if self.arena is None:
-            self.arena = Arena(self.device)
-            self.zarena = Arena(self.device)
-            self.zarena.CHUNK = 8 << 20
+    def _select_arenas(self, which):
+        if which not in self._arenas:
+            a, z = Arena(self.device), Arena(self.device)
+            z.CHUNK = 8 << 20
+            self._arenas[which] = (a, z)
+        self.arena, self.zarena = self._arenas[which]
+
+    def begin_step(self, record=True):
+        """Reset the bump allocators; the zero-initialised region (BN / reduction accumulators, wgrad tickets) is
+        cleared with ONE memset per chunk instead of one per buffer.  Forwards that keep nothing for a backward
+        (eval, no_grad) run in their own arenas, so they never overwrite the activations of a pending backward."""
+        self._select_arenas("train" if record else "eval")
         self.arena.reset()
         self.zarena.reset()
         for t, _, _ in self.zarena.chunks:
             t.zero_()
-        self._zchunks_zeroed = len(self.zarena.chunks)
+        self.zarena.zeroed = len(self.zarena.chunks)
 
     def new(self, N, H, W, C, ld=None):
         ld = ld or C
@@ -128,12 +144,29 @@ class UNetEngine:
         if zero:
             first = self.zarena.cur >= len(self.zarena.chunks)
             ptr = self.zarena.alloc(nb)
-            if first or self.zarena.cur >= self._zchunks_zeroed:
+            if first or self.zarena.cur >= self.zarena.zeroed:
                 # chunk created after begin_step's memset: clear it once now
                 self.zarena.chunks[self.zarena.cur][0].zero_()
-                self._zchunks_zeroed = self.zarena.cur + 1
+                self.zarena.zeroed = self.zarena.cur + 1
             return ptr
         return self.arena.alloc(nb)
+
+    # ------------------------------------------------------------------ side stream for weight gradients
+    def _wgrad_stream(self):
+        """stream handle for a weight-gradient kernel: the side stream, made to wait for all work issued on the
+        main stream so far (the kernel's inputs), or the main stream when the overlap is disabled"""
+        if not self.side_wgrad:
+            return self.stream
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        self._side.wait_stream(self._main_obj)
+        self._side_used = True
+        return self._side.cuda_stream
+
+    def _join_side(self):
+        if self.side_wgrad and self._side is not None and getattr(self, "_side_used", False):
+            self._main_obj.wait_stream(self._side)
+            self._side_used = False
 
     # ------------------------------------------------------------------ gradient routing
     def _grad_dst(self, x):
@@ -211,12 +244,15 @@ class UNetEngine:
         ent = self._packs.get(key)
         w = self.p[wname]
         cout, cin = w.shape[0], w.shape[1]
+        created = ent is None
         if ent is None:
             rows, cols = (cpad_in, cpad_out) if flip else (cpad_out, cpad_in)
             buf = torch.empty(rows * k * k * cols, dtype=torch.bfloat16, device=self.device)
             ent = self._packs[key] = (buf, (w.data_ptr(), buf.data_ptr(), cout, cin, k * k, flip, cpad_in, cpad_out))
             self._pack_table = None                      # plan changed: rebuild the device table
-        if not self._packed_this_step:
+        # a packing requested for the first time (a new input size made another layer eligible for the tensor
+        # path after the plan was complete) is NOT in this step's batched re-pack: fill it now
+        if created or not self._packed_this_step:
             call("sc_tc_pack_weights", w.data_ptr(), ent[0].data_ptr(), cout, cin, k, k, flip, cpad_in, cpad_out, self.stream)
         return ent[0].data_ptr()
 
@@ -288,12 +324,18 @@ class UNetEngine:
         cout, cin = w.shape[0], w.shape[1]
         pad = k // 2
         tc = self._tc_ok(x, cin, cout, k, stride) and dy.ld % 8 == 0
+        lib = _lib.load()
         if tc:
-            call("sc_tc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), x.N, x.H, x.W, cin, cout,
-                 k, k, stride, self.stream)
+            # deterministic split-K: partial tiles in a workspace, summed in split order by a second kernel
+            nb = lib.sc_tc_conv_wgrad_workspace_bytes(x.N, x.H, x.W, cin, cout, k, k, stride)
+            part = self.arena.alloc(nb) if nb > 0 else 0
+            call("sc_tc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), part, x.N, x.H, x.W,
+                 cin, cout, k, k, stride, self._wgrad_stream())
         else:
-            call("sc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), x.N, x.H, x.W, cin, cout,
-                 k, k, stride, pad, self.dtype, self.stream)
+            nb = lib.sc_conv_wgrad_workspace_bytes(x.N, x.H, x.W, cin, cout, k, k, stride, pad)
+            part = self.arena.alloc(nb) if nb > 0 else 0
+            call("sc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), part, x.N, x.H, x.W, cin, cout,
+                 k, k, stride, pad, self.dtype, self._wgrad_stream())
         if need_dx:
             assert stride == 1
             dst, acc = self._grad_dst(x)
@@ -360,7 +402,7 @@ class UNetEngine:
                 dy2 = self._bn_backward(z2, y2, bn2, st2, ACT_RELU6, False)
                 ws = self.arena.alloc(_lib.load().sc_dwconv_wgrad_workspace_bytes(hidden))
                 call("sc_dwconv_wgrad", dw_in.ptr, dw_in.ld, dw_scale, dw_shift, dw_act, dy2.ptr, dy2.ld,
-                     self.g[wdw].data_ptr(), ws, x.N, x.H, x.W, hidden, stride, self.dtype, self.stream)
+                     self.g[wdw].data_ptr(), ws, x.N, x.H, x.W, hidden, stride, self.dtype, self._wgrad_stream())
                 if use_res:
                     self._alias_grad(x, z3.grad)        # d(x + f(x)) -> x gets dz3 as is
                 if t != 1:
@@ -394,6 +436,10 @@ class UNetEngine:
             raise _lib.StarcopB200Error("backward through eval-mode BatchNorm is not implemented: call .train() before a step that needs gradients")
         N, H, W = x_nhwc.N, x_nhwc.H, x_nhwc.W
         assert H % 32 == 0 and W % 32 == 0, "input height and width must be divisible by 32 (smp check_input_shape)"
+        tape_keep = (self.tape, getattr(self, "_head_in", None))
+        if self.record:
+            self.generation += 1
+            self._tape_generation = self.generation
         self.tape = []
         if self.use_tc:
             self._pack_all()
@@ -447,21 +493,34 @@ class UNetEngine:
         call("sc_head_fprop", z.ptr, z.ld, hw.data_ptr(), hb.data_ptr(), logits_ptr, N, H, W, z.C, self.dtype, self.stream)
         if self.record:
             self._head_in = z
+        else:
+            self.tape, self._head_in = tape_keep       # a pending backward keeps its tape
         return cat
 
-    def backward(self, dlogits_ptr):
+    def backward(self, dlogits_ptr, generation=None):
+        """generation: the value of `self.generation` right after the forward this backward belongs to."""
+        if generation is not None and generation != self.generation:
+            raise _lib.StarcopB200Error(
+                "backward() of a forward whose activations were overwritten by a later recording forward: the "
+                "engine keeps ONE set of activations (call backward before the next training forward)")
+        if self._tape_generation != self.generation or not self.tape:
+            raise _lib.StarcopB200Error("backward() called twice for one forward (retain_graph is not supported)")
+        self._select_arenas("train")
+        self._main_obj = torch.cuda.current_stream(self.device)
         z = self._head_in
         z.grad = self.new_like(z)
         hw = self.p["segmentation_head.0.weight"]
         # data gradient by the per-pixel kernel; weight / bias gradient by the TMA tile kernel (partial rows)
-        call("sc_head_bwd", z.ptr, z.ld, hw.data_ptr(), dlogits_ptr, z.grad.ptr, z.grad.ld, 0, 0,
+        call("sc_head_bwd", z.ptr, z.ld, hw.data_ptr(), dlogits_ptr, z.grad.ptr, z.grad.ld,
              z.N, z.H, z.W, z.C, self.dtype, self.stream)
         ws = self.arena.alloc(_lib.load().sc_head_wgrad_workspace_bytes(z.C))
         call("sc_head_wgrad_tiled", z.ptr, z.ld, dlogits_ptr, self.g["segmentation_head.0.weight"].data_ptr(),
-             self.g["segmentation_head.0.bias"].data_ptr(), ws, z.N, z.H, z.W, z.C, self.dtype, self.stream)
+             self.g["segmentation_head.0.bias"].data_ptr(), ws, z.N, z.H, z.W, z.C, self.dtype, self._wgrad_stream())
         for fn in reversed(self.tape):
             fn()
+        self._join_side()
         self.tape = []
+        self._tape_generation = -1
         self._plan_complete = True          # every fprop and dgrad packing request of the network is now recorded
         if self._packs and self._pack_table is None:
             self._build_pack_table()

@@ -84,7 +84,8 @@ def get_mask_bad_bands(wave):
 def band_keep_aviris(wavelengths):
     """process_aviris.py:192-206: the matched-filter window as ONE contiguous slice."""
     wavelengths = np.asarray(wavelengths)
-    keep = get_mask_bad_bands(wavelengths) & (wavelengths > 2122) & (wavelengths < 2488)
+    # band_keep[wavelengths < lo] = False; band_keep[wavelengths > hi] = False  -> the bounds themselves are kept
+    keep = get_mask_bad_bands(wavelengths) & (wavelengths >= 2122) & (wavelengths <= 2488)
     idx = np.where(keep)[0]
     if not len(idx) or np.any(np.diff(idx) != 1):
         raise AssertionError("Selected bands are not contiguous")
@@ -116,6 +117,10 @@ def acrwl1mf(x, template, num_iter=30, alpha=0., check=True):
     assert x.dim() == 3, "x must be [batch(groups), pixels, spectrum]"
     x = x.contiguous()
     b, p, s = x.shape
+    if p <= 10:
+        # the kernel skips groups of <= 10 pixels (func_by_groups' rule, mag1c.py:166-168); a DIRECT call with so few
+        # pixels has a rank-deficient covariance (p < s): the reference raises from torch.linalg.cholesky there
+        raise torch.linalg.LinAlgError(f"linalg.cholesky: covariance of {p} pixels x {s} bands is not positive-definite")
     idx = torch.arange(b * p, dtype=torch.int32, device=x.device).view(b, p)
     mf = torch.empty(b, p, 1, dtype=x.dtype, device=x.device)
     al = torch.empty_like(mf)
@@ -186,8 +191,10 @@ def mag1c_tiles(cube, template, band_slice, num_iter=30, alpha=0.):
     n, H, W, C = cube.shape
     S = band_slice.stop - band_slice.start
     idx = _column_groups(n, H, W, cube.device)
-    mf = torch.empty(n, H, W, dtype=cube.dtype, device=cube.device)
-    al = torch.empty_like(mf)
+    # groups (columns) of <= 10 pixels are skipped like func_by_groups does: their outputs keep the NODATA fill
+    mk = torch.full if H <= 10 else (lambda shape, _v, **kw: torch.empty(shape, **kw))
+    mf = mk((n, H, W), float(NODATA), dtype=cube.dtype, device=cube.device)
+    al = mk((n, H, W), float(NODATA), dtype=cube.dtype, device=cube.device)
     xw = cube.view(-1)[band_slice.start:]          # same storage, offset to the first window band
     _filter(xw, C, idx, None, template, mf, al, S, num_iter, alpha)
     return mf, al

@@ -40,13 +40,14 @@ class _UnetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, net, x, norm, *params):
         ctx.net = net
-        ctx.training = True
-        return net._forward_impl(x, norm, net.training, record=True)
+        out = net._forward_impl(x, norm, net.training, record=True)
+        ctx.generation = net._engine.generation        # the activations this node's backward needs
+        return out
 
     @staticmethod
     def backward(ctx, dlogits):
         net = ctx.net
-        net._backward_impl(dlogits)
+        net._backward_impl(dlogits, ctx.generation)     # raises if a later recording forward replaced them
         return (None, None, None, *net._grad_views)
 
 
@@ -121,7 +122,7 @@ class HyperStarcopUnet(UnetParameters):
             raise RuntimeError(f"Wrong input shape height={H}, width={W}. Expected image height and width "
                                f"divisible by 32.")
         eng.stream = _stream(x.device)
-        eng.begin_step()
+        eng.begin_step(record=training if record is None else record)
         ldin = C if eng.dtype == _lib.SC_F32 else (C + 7) // 8 * 8
         xin = eng.new(B, H, W, C, ld=ldin)
         if norm is None:
@@ -138,12 +139,12 @@ class HyperStarcopUnet(UnetParameters):
             torch._foreach_add_(self._nbt, 1)
         return logits
 
-    def _backward_impl(self, dlogits):
+    def _backward_impl(self, dlogits, generation=None):
         eng = self._engine
         self._flat[1].zero_()
         d = dlogits.contiguous().float()
         eng.stream = _stream(d.device)
-        eng.backward(d.data_ptr())
+        eng.backward(d.data_ptr(), generation)
 
     def _identity_norm(self, device, C):
         key = (str(device), C)
@@ -160,7 +161,9 @@ class HyperStarcopUnet(UnetParameters):
         if squeeze:
             x = x[None]
         params = list(self.parameters())
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        # eval-mode forwards never record (the reference allows `model.eval(); model(x)` without no_grad();
+        # gradients through running-statistics BatchNorm are not part of the hot path)
+        need_grad = self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params)
         if need_grad:
             out = _UnetFunction.apply(self, x, _norm, *params)
         else:
@@ -235,20 +238,26 @@ class HyperStarcopUnet(UnetParameters):
 # --------------------------------------------------------------------------------------------------
 # loss: BCEWithLogitsLoss(pos_weight, reduction) + mean(loss * weight_loss), one fused kernel
 # --------------------------------------------------------------------------------------------------
+def _loss_buffer(B, HW, device):
+    """sc_bce_fused's loss accumulator: [0] the fp64 sum, [1] a ticket word, [2:] per-block partials (the kernel
+    adds the partials up in block order: deterministic).  Zero-filled, as the C ABI requires of [0] and [1]."""
+    return torch.zeros(_lib.load().sc_bce_loss_words(B, HW), dtype=torch.float64, device=device)
+
+
 class _WeightedBCEFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, y, w, pos_weight):
         lg = logits.contiguous().float()
         B = lg.shape[0]
         HW = lg.numel() // B
-        loss_sum = torch.zeros(1, dtype=torch.float64, device=lg.device)
+        loss_sum = _loss_buffer(B, HW, lg.device)
         grad = torch.empty_like(lg) if ctx.needs_input_grad[0] else None
         _lib.call("sc_bce_fused", lg.data_ptr(), y.contiguous().float().data_ptr(),
                   w.contiguous().float().data_ptr() if w is not None else 0, float(pos_weight), B, HW,
                   1.0 / lg.numel(), loss_sum.data_ptr(), grad.data_ptr() if grad is not None else 0,
                   0, 0, 0, 0, 0, 0, 0, 0, 0, _stream(lg.device))
         ctx.save_for_backward(grad)
-        return (loss_sum / lg.numel()).float()[0]
+        return (loss_sum[0] / lg.numel()).float()
 
     @staticmethod
     def backward(ctx, gout):
@@ -432,13 +441,13 @@ class ModelModule(_Base):
             B = logits.shape[0]
             HW = logits.numel() // B
             dev = logits.device
-            loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+            loss_sum = _loss_buffer(B, HW, dev)
             cm = torch.zeros(4, dtype=torch.long, device=dev)
             cnt = torch.zeros(B, dtype=torch.long, device=dev)
             _lib.call("sc_bce_fused", logits.data_ptr(), y.data_ptr(), w.data_ptr() if w is not None else 0,
                       self._pw(), B, HW, 0.0, loss_sum.data_ptr(), 0, cm.data_ptr(), cnt.data_ptr(),
                       0, 0, 0, 0, 0, 0, 0, _stream(dev))
-            loss = (loss_sum / logits.numel()).float()[0]
+            loss = (loss_sum[0] / logits.numel()).float()
             self.log(f"{prefix}_loss", loss, on_epoch=True)
             if self.settings_model.model_mode == "segmentation_output":
                 self.confusion_matrix.add_counts(cm)
@@ -530,7 +539,7 @@ class ModelModule(_Base):
         B = logits.shape[0]
         n = logits.numel()
         dev = logits.device
-        loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        loss_sum = _loss_buffer(B, n // B, dev)
         grad = torch.empty_like(logits)
         _lib.call("sc_bce_fused", logits.data_ptr(), y.contiguous().float().data_ptr(),
                   w.contiguous().float().data_ptr() if w is not None else 0, self._pw(), B, n // B,
@@ -540,7 +549,7 @@ class ModelModule(_Base):
         if grad_sync is not None:
             scale = grad_sync(net.flat_grads)
         net.adam_step(self.lr if lr is None else lr, grad_scale=scale)
-        return (loss_sum / n).float()[0]
+        return (loss_sum[0] / n).float()
 
     def make_graphed_train_step(self, example_batch, grad_sync=None, warmup=2, double_buffer=False):
         """Capture train_step_fused into ONE CUDA graph (every buffer of the step comes from the static

@@ -63,7 +63,9 @@ class DataNormalizer(torch.nn.Module):
 
     def kernel_params(self, device):
         """(4,C) float64 device tensor [off, fac, lo, hi] + the float64 promotion mask."""
-        key = (str(device), self.offsets_input.data_ptr())
+        # keyed on the parameters' storage AND version counters: load_state_dict / in-place edits invalidate it
+        prm = (self.offsets_input, self.factors_input, self.clip_min_input, self.clip_max_input)
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in prm)
         if self._dev_params is None or self._dev_params[0] != key:
             arr = torch.stack([t.detach().reshape(-1).to(torch.float64) for t in
                                (self.offsets_input, self.factors_input, self.clip_min_input, self.clip_max_input)])

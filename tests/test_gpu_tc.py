@@ -7,6 +7,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
+from starcop_b200 import ops  # noqa: E402
 from starcop_b200._lib import call, load  # noqa: E402
 
 DEV = "cuda"
@@ -92,13 +93,20 @@ def test_tc_wgrad(N, H, W, Cin, Cout, k):
     x, w = make(N, H, W, Cin, Cout, k, seed=1)
     dy = torch.randn(N, H, W, Cout, device=DEV).to(torch.bfloat16)
     dw = torch.zeros(Cout, Cin, k, k, device=DEV)
-    call("sc_tc_conv_wgrad", x.data_ptr(), Cin, dy.data_ptr(), Cout, dw.data_ptr(), N, H, W, Cin, Cout, k, k, 1, st())
+    ws = ops.tc_conv_wgrad(x, Cin, dy, Cout, dw, N, H, W, Cin, Cout, k)
     torch.cuda.synchronize()
     wr = w.clone().requires_grad_(True)
     yr = F.conv2d(x.float().permute(0, 3, 1, 2), wr, padding=k // 2)
     (gw,) = torch.autograd.grad(yr, wr, dy.float().permute(0, 3, 1, 2))
     err = (dw - gw).abs().max().item()
     assert err <= 2e-3 * gw.abs().max().item(), (err, gw.abs().max().item())
+    # deterministic split-K: a second launch (same workspace: the tickets must be back at zero) is bit-identical,
+    # and the gradient is accumulated onto what is there
+    dw2 = torch.zeros_like(dw)
+    ops.tc_conv_wgrad(x, Cin, dy, Cout, dw2, N, H, W, Cin, Cout, k, workspace=ws)
+    assert torch.equal(dw, dw2)
+    ops.tc_conv_wgrad(x, Cin, dy, Cout, dw2, N, H, W, Cin, Cout, k, workspace=ws)
+    assert torch.allclose(dw2, 2 * dw, rtol=1e-6, atol=0)
 
 
 def test_tc_stem_stride2_fprop_and_wgrad():
@@ -119,7 +127,7 @@ def test_tc_stem_stride2_fprop_and_wgrad():
     assert torch.allclose(y.float(), ref.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
     dy = torch.randn(N, H // 2, W // 2, Cout, device=DEV).to(torch.bfloat16)
     dw = torch.zeros(Cout, Cin, k, k, device=DEV)
-    call("sc_tc_conv_wgrad", x8.data_ptr(), 8, dy.data_ptr(), Cout, dw.data_ptr(), N, H, W, Cin, Cout, k, k, 2, st())
+    ops.tc_conv_wgrad(x8, 8, dy, Cout, dw, N, H, W, Cin, Cout, k, stride=2)
     (gw,) = torch.autograd.grad(ref, wr, dy.float().permute(0, 3, 1, 2))
     assert (dw - gw).abs().max().item() <= 2e-3 * gw.abs().max().item()
 

@@ -206,10 +206,30 @@ def test_requires_cuda_and_divisible_by_32():
         model(torch.zeros(1, 4, 64, 64))           # CPU tensor: no CPU path
 
 
-def test_graphed_train_step_matches_eager():
-    """The CUDA-graph replay of the fused step is the same computation as launching it eagerly."""
-    _, m1 = build_pair(1.0)
-    _, m2 = build_pair(1.0)
+@pytest.mark.parametrize("compute_dtype", ["f32", "bf16"])
+def test_train_step_is_bit_reproducible(compute_dtype):
+    """No floating-point atomics anywhere in the step (weight gradients: per-split partial tiles summed in split
+    order; BatchNorm: partial rows; loss: block partials summed in block order): two runs from the same weights on
+    the same batch give bit-identical gradients, losses and updated parameters."""
+    outs = []
+    for _ in range(2):
+        _, m = build_pair(1.0, compute_dtype=compute_dtype)
+        m.train()
+        losses = []
+        for s_ in range(2):
+            b = to_dev(synthetic.hyperstarcop_batch(2, size=96, seed=30 + s_))
+            losses.append(m.train_step_fused(b))
+        outs.append((torch.stack(losses).clone(), m.network.flat_grads.clone(), m.network.flat_params.clone()))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("compute_dtype", ["f32", "bf16"])
+def test_graphed_train_step_matches_eager(compute_dtype):
+    """The CUDA-graph replay of the fused step is the same computation as launching it eagerly: after three
+    optimisation steps the two models hold BIT-IDENTICAL parameters (the step is deterministic)."""
+    _, m1 = build_pair(1.0, compute_dtype=compute_dtype)
+    _, m2 = build_pair(1.0, compute_dtype=compute_dtype)
     m1.train(); m2.train()
     b0 = to_dev(synthetic.hyperstarcop_batch(2, size=64, seed=20))
     m1.train_step_fused(b0)                                  # the graph builder runs one eager warm-up step
@@ -218,11 +238,109 @@ def test_graphed_train_step_matches_eager():
         b = to_dev(synthetic.hyperstarcop_batch(2, size=64, seed=20 + s))
         l1 = m1.train_step_fused(b)
         l2 = step(b)
-        # step 0 starts from identical weights; afterwards fp32-atomic summation order in the weight
-        # gradients + Adam's sign-like first updates let the two runs drift by ~1e-4 (see the Adam test)
-        assert abs(l1.item() - l2.item()) <= (1e-6 if s == 0 else 2e-3) * abs(l1.item()), (s, l1.item(), l2.item())
-    assert (m1.network.flat_params - m2.network.flat_params).abs().mean().item() < 1e-4
+        assert l1.item() == l2.item(), (s, l1.item(), l2.item())
+    assert torch.equal(m1.network.flat_params, m2.network.flat_params)
+    for (n, b1), (_, b2) in zip(m1.network.named_buffers(), m2.network.named_buffers()):
+        assert torch.equal(b1, b2), n
     assert int(m2.network._adam_state["step"].item()) == 4   # one eager warm-up + 3 replays (capture records, it does not execute)
+
+
+def test_lr_scheduler_drives_the_fused_step():
+    """ReduceLROnPlateau (model_module.py:178-185) on the fused / graphed step: the scheduler's learning rate is
+    pushed to the device-resident lr with set_lr, the captured graph picks it up without re-capture."""
+    _, m = build_pair(1.0)
+    m.train()
+    b = to_dev(synthetic.hyperstarcop_batch(2, size=64, seed=21))
+    step = m.make_graphed_train_step(b, warmup=1)
+    cfg = m.configure_optimizers()
+    sched, opt = cfg["lr_scheduler"], cfg["optimizer"]
+    assert isinstance(sched, torch.optim.lr_scheduler.ReduceLROnPlateau)
+    step(b)
+    p0 = m.network.flat_params.clone()
+    for _ in range(m.lr_patience + 2):                      # a flat val_loss: the plateau scheduler halves the lr once
+        sched.step(1.0)
+    new_lr = opt.param_groups[0]["lr"]
+    assert abs(new_lr - m.lr * m.lr_decay) <= 1e-12
+    m.network.set_lr(new_lr)
+    step(b)
+    d_small = (m.network.flat_params - p0).abs().max().item()
+    m.network.set_lr(0.0)
+    p1 = m.network.flat_params.clone()
+    step(b)
+    assert torch.equal(m.network.flat_params, p1)           # lr = 0: the replayed graph reads the device lr
+    assert 0 < d_small <= 4 * new_lr                        # |Adam update| <= lr * (1-b1)/sqrt(1-b2) per element
+
+
+def test_eval_forward_between_forward_and_backward_keeps_the_tape():
+    """an eval / no_grad forward (logging, batch_with_preds) between training_step and .backward() must
+    not clobber the pending backward's activations; a second RECORDING forward must make the stale backward fail
+    loudly instead of computing garbage."""
+    _, m1 = build_pair(1.0)
+    _, m2 = build_pair(1.0)
+    m1.train(); m2.train()
+    b = to_dev(synthetic.hyperstarcop_batch(2, size=64, seed=22))
+    other = to_dev(synthetic.hyperstarcop_batch(2, size=64, seed=23))
+    l1 = m1.training_step(b, 0); l1.backward()
+    l2 = m2.training_step(b, 0)
+    with torch.no_grad():
+        m2(other["input"])                                   # train-mode no_grad forward
+    m2.eval()
+    m2.batch_with_preds(other)                               # eval forward
+    out = m2(other["input"])                                 # eval forward WITHOUT no_grad (reference allows it)
+    assert not out.requires_grad
+    m2.train()
+    l2.backward()
+    for (n, p1), (_, p2) in zip(m1.network.named_parameters(), m2.network.named_parameters()):
+        assert torch.equal(p1.grad, p2.grad), n
+    la = m2.training_step(b, 0)
+    lb = m2.training_step(other, 0)
+    with pytest.raises(Exception, match="overwritten"):
+        la.backward()
+    lb.backward()
+
+
+def test_bf16_size_change_after_plan_complete():
+    """layers that become tensor-core eligible only at a larger input size (the 1/16 and 1/32
+    resolution layers fail W % 16 at 128 x 128) get their bf16 weight packing the first time they are requested,
+    even though the step's batched re-pack has already run."""
+    _, mb = build_pair(1.0, compute_dtype="bf16")
+    _, mf = build_pair(1.0, compute_dtype="f32")
+    small = to_dev(synthetic.hyperstarcop_batch(2, size=128, seed=24))
+    big = to_dev(synthetic.hyperstarcop_batch(2, size=512, seed=25))
+    mb.train(); mf.train()
+    for m in (mb, mf):
+        m.train_step_fused(small)
+        m.train_step_fused(small)                            # plan complete, batched re-pack active
+    mb.eval(); mf.eval()
+    with torch.no_grad():
+        lb, lf = mb(big["input"]), mf(big["input"])
+    assert torch.isfinite(lb).all()
+    assert (torch.sigmoid(lb) - torch.sigmoid(lf)).abs().max().item() <= 5e-2
+    mb.train(); mf.train()
+    l_b, l_f = mb.train_step_fused(big), mf.train_step_fused(big)
+    assert abs(l_b.item() - l_f.item()) <= 3e-2 * abs(l_f.item())
+    assert torch.isfinite(mb.network.flat_params).all() and torch.isfinite(mb.network.flat_grads).all()
+    gb = dict(mb.network.named_parameters())
+    gf = dict(mf.network.named_parameters())
+    cos = lambda a, b: torch.nn.functional.cosine_similarity(a.flatten().double(), b.flatten().double(), dim=0).item()
+    i = list(gb).index("segmentation_head.0.weight")
+    assert cos(mb.network._grad_views[i], mf.network._grad_views[i]) > 0.99
+
+
+def test_normalizer_cache_follows_load_state_dict():
+    """the fused normalise kernel must see parameters loaded / edited in place."""
+    _, m = build_pair(1.0)
+    m.eval()
+    b = to_dev(synthetic.hyperstarcop_batch(1, size=64, seed=26))
+    with torch.no_grad():
+        a = m.normalizer.normalize_x(b["input"]).clone()
+        sd = m.state_dict()
+        sd["normalizer.factors_input"] = sd["normalizer.factors_input"] * 2
+        m.load_state_dict(sd)
+        c = m.normalizer.normalize_x(b["input"])
+    ref = torch.clamp(b["input"] / (torch.tensor([1750., 60., 60., 60.], device=DEV) * 2)[None, :, None, None], 0, 2)
+    assert not torch.equal(a, c)
+    assert torch.allclose(c, ref, rtol=1e-6, atol=0)
 
 
 def test_graphed_step_prefetch_from_pinned_host_matches_direct_stepping():
@@ -271,8 +389,11 @@ def test_per_tile_validation_and_padded_predict():
             bo = oracle.batch_with_preds(t)
         safe = bo["logits"].abs() > 1e-3
         cm_o = olm.confusion_matrix(bo["pred_binary"], bo["output_norm"].long())
-        if bool(safe.all()):
-            assert row["TP"] == int(cm_o[1, 1]) and row["FP"] == int(cm_o[0, 1])
+        # pixels whose oracle logit lies within the fp32 tolerance of 0 may flip: they bound the count difference
+        unsafe = int((~safe).sum())
+        assert abs(row["TP"] - int(cm_o[1, 1])) <= unsafe and abs(row["FP"] - int(cm_o[0, 1])) <= unsafe
+        assert abs(row["FN"] - int(cm_o[1, 0])) <= unsafe and abs(row["TN"] - int(cm_o[0, 0])) <= unsafe
+        assert row["TP"] + row["FP"] + row["FN"] + row["TN"] == 64 * 64
         assert row["label_pixels_plume"] == int(t["output"].sum())
         assert row["pred_classification"] == int(bo["pred_classification"][0, 0])
         tot += cm_o
