@@ -18,6 +18,7 @@
  *   STARCOP_MAG1C_STREAMING  sc_mag1c_filter: always the streaming kernel (no group-resident fast path)
  *   STARCOP_RATIO_NOCLUSTER / STARCOP_RATIO_CLUSTER   sc_ratio_product: force the single-CTA / the cluster select
  *   STARCOP_BN_NOFLAT        sc_bn_bwd_reduce: always the register-streaming kernel (no cp.async.bulk ring)
+ *   STARCOP_NO_WGRAD_HALO    sc_tc_conv_wgrad: always the per-tap kernel (no halo-patch kernel for the thin layers)
  */
 #ifndef STARCOP_B200_H
 #define STARCOP_B200_H
@@ -241,6 +242,17 @@ int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void* y, int ld
 int64_t sc_tc_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride);
 int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, float* partials,
                      int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride, void* stream);
+
+/* Thin-layer weight gradient (3x3, stride 1, pad 1; Cin >= 16, Cout in {16, 32}, H % 8 == 0, W % 16 == 0): the halo
+ * patch of a 16x8 pixel tile is fetched once per 32-channel group and the horizontal taps are stacked along the MMA's
+ * M dimension (one pixel of descriptor stride per tap), ~4x fewer TMA rows than one shifted box per tap.  One partial
+ * gradient per CTA in `partials` (sc_tc_wgrad_halo_workspace_bytes), summed in CTA order: deterministic.
+ * sc_tc_conv_wgrad dispatches here by itself when sc_tc_wgrad_halo_supported(...) (its workspace query covers it);
+ * STARCOP_NO_WGRAD_HALO=1 disables the route. */
+int sc_tc_wgrad_halo_supported(int N, int H, int W, int Cin, int Cout);
+int64_t sc_tc_wgrad_halo_workspace_bytes(int N, int H, int W, int Cin, int Cout);
+int sc_tc_wgrad_halo(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, float* partials,
+                     int N, int H, int W, int Cin, int Cout, void* stream);
 
 /* Thin-layer variant for 3x3 / stride 1 / pad 1 (decoder blocks 2-4, fprop and dgrad): the 18x10 input halo
  * patch of a 16x8 pixel tile is staged ONCE (9x less L2->SM traffic than one shifted box per tap) and all nine

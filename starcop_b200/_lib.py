@@ -61,11 +61,14 @@ SIGNATURES = {
     "sc_tc_halo_supported": [I, I],
     "sc_tc_conv3x3_halo": [P, I, P, P, I, P, P, I, I, I, I, I, I, P],
     "sc_tc_conv_wgrad_workspace_bytes": [I, I, I, I, I, I, I, I],
+    "sc_tc_wgrad_halo_supported": [I, I, I, I, I],
+    "sc_tc_wgrad_halo_workspace_bytes": [I, I, I, I, I],
+    "sc_tc_wgrad_halo": [P, I, P, I, P, P, I, I, I, I, I, P],
     "sc_tc_conv_wgrad": [P, I, P, I, P, P, I, I, I, I, I, I, I, I, P],
 }
 _RESTYPES = {"sc_last_cuda_error": ctypes.c_char_p, "sc_mag1c_smem_bytes": c_int64, "sc_bn_partials_bytes": c_int64, "sc_mlr_workspace_bytes": c_int64, "sc_dwconv_wgrad_workspace_bytes": c_int64, "sc_head_wgrad_workspace_bytes": c_int64,
              "sc_ratio_workspace_bytes": c_int64, "sc_conv_wgrad_workspace_bytes": c_int64,
-             "sc_tc_conv_wgrad_workspace_bytes": c_int64, "sc_bce_loss_words": c_int64}
+             "sc_tc_conv_wgrad_workspace_bytes": c_int64, "sc_tc_wgrad_halo_workspace_bytes": c_int64, "sc_bce_loss_words": c_int64}
 
 _lib = None
 

@@ -759,6 +759,8 @@ static int wgrad_geometry(int N, int Ho, int Wo, int Cin, int Cout, int KH, int 
 extern "C" int64_t sc_tc_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
   const int Ho = stride == 1 ? H : (H + 2 * (KH / 2) - KH) / 2 + 1;
   const int Wo = stride == 1 ? W : (W + 2 * (KW / 2) - KW) / 2 + 1;
+  if (KH == 3 && KW == 3 && stride == 1 && sc_tc_wgrad_halo_supported(N, H, W, Cin, Cout))
+    return sc_tc_wgrad_halo_workspace_bytes(N, H, W, Cin, Cout);
   WgradParams p;
   int kc;
   if (Cin < 1 || wgrad_geometry(N, Ho, Wo, Cin, Cout, KH, KW, &p, &kc) != SC_OK) return -1;
@@ -773,6 +775,8 @@ extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy
   const int Wo = stride == 1 ? W : (W + 2 * (KW / 2) - KW) / 2 + 1;
   if (Cin < 1 || Cout % 8 || Wo % 16 || Ho % 4 || ldx % 8 || lddy % 8 || KH != KW || (KH != 1 && KH != 3))
     return SC_ERR_UNSUPPORTED;
+  if (KH == 3 && stride == 1 && sc_tc_wgrad_halo_supported(N, H, W, Cin, Cout))      // thin layers: halo-patch kernel
+    return sc_tc_wgrad_halo(x, ldx, dy, lddy, dw_oihw, partials, N, H, W, Cin, Cout, stream);
   WgradParams p;
   int kc;
   p.N = N; p.H = Ho; p.W = Wo; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.stride = stride;

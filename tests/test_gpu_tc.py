@@ -191,3 +191,40 @@ def test_tc_halo_dgrad_via_flipped_weights():
     yr = F.conv2d(xr, w.to(torch.bfloat16).float(), padding=1)
     (gx,) = torch.autograd.grad(yr, xr, dy.float().permute(0, 3, 1, 2))
     assert torch.allclose(dx.float(), gx.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 32, 16, 16), (2, 32, 32, 32, 16), (2, 16, 16, 32, 32), (1, 24, 48, 80, 32),
+                                            (3, 8, 16, 16, 32), (2, 40, 64, 24, 16), (16, 64, 64, 32, 16)])
+def test_tc_wgrad_halo(N, H, W, Cin, Cout, monkeypatch):
+    """thin-layer weight gradient: halo patch fetched once, horizontal taps stacked along the MMA's M dimension.
+    Against PyTorch fp32 on the same bf16 operands, against the per-tap tcgen05 kernel, and bit-reproducible."""
+    lib = load()
+    assert lib.sc_tc_wgrad_halo_supported(N, H, W, Cin, Cout) == 1
+    torch.manual_seed(11)
+    x = torch.randn(N, H, W, Cin, device=DEV).to(torch.bfloat16)
+    dy = torch.randn(N, H, W, Cout, device=DEV).to(torch.bfloat16)
+    dw = torch.zeros(Cout, Cin, 3, 3, device=DEV)
+    ws = ops.tc_conv_wgrad(x, Cin, dy, Cout, dw, N, H, W, Cin, Cout, 3)
+    wr = torch.zeros(Cout, Cin, 3, 3, device=DEV, requires_grad=True)
+    yr = F.conv2d(x.float().permute(0, 3, 1, 2), wr, padding=1)
+    (gw,) = torch.autograd.grad(yr, wr, dy.float().permute(0, 3, 1, 2))
+    scale = gw.abs().max().item()
+    assert (dw - gw).abs().max().item() <= 2e-3 * scale, ((dw - gw).abs().max().item(), scale)
+    dw2 = torch.zeros_like(dw)
+    ops.tc_conv_wgrad(x, Cin, dy, Cout, dw2, N, H, W, Cin, Cout, 3, workspace=ws)
+    assert torch.equal(dw, dw2)
+    monkeypatch.setenv("STARCOP_NO_WGRAD_HALO", "1")
+    assert lib.sc_tc_wgrad_halo_supported(N, H, W, Cin, Cout) == 0
+    dw3 = torch.zeros_like(dw)
+    ops.tc_conv_wgrad(x, Cin, dy, Cout, dw3, N, H, W, Cin, Cout, 3)
+    assert (dw - dw3).abs().max().item() <= 1e-4 * scale      # same bf16 products, fp32 accumulation order differs
+    # channel-slice operands (explicit ld): x is a slice of a wider concat buffer
+    monkeypatch.delenv("STARCOP_NO_WGRAD_HALO")
+    wide = torch.randn(N, H, W, Cin + 16, device=DEV).to(torch.bfloat16)
+    wide[..., 8:8 + Cin] = x
+    dw4 = torch.zeros_like(dw)
+    xs = wide[..., 8:]
+    lib_ws = torch.empty(max(lib.sc_tc_conv_wgrad_workspace_bytes(N, H, W, Cin, Cout, 3, 3, 1), 4), dtype=torch.uint8, device=DEV)
+    call("sc_tc_conv_wgrad", xs.data_ptr(), Cin + 16, dy.data_ptr(), Cout, dw4.data_ptr(), lib_ws.data_ptr(), N, H, W, Cin, Cout,
+         3, 3, 1, st())
+    assert torch.equal(dw, dw4)
