@@ -171,8 +171,11 @@ def gpu_eager_baseline(dev, B, S, steps=5, warmup=3):
 
 
 def mode_parity(dev, S):
-    """sigmoid-map / loss difference between the benchmarked bf16 tcgen05 mode and the fp32 parity mode (which
-    tests/test_gpu_parity512.py pins to the fp32 oracle at this tile size within 1e-4) on 2 tiles, train-mode BN."""
+    """Distance between the benchmarked bf16 tcgen05 mode and the fp32 parity mode (which tests/test_gpu_parity512.py
+    pins to the fp32 oracle at this tile size) on 2 tiles, same weights: eval-mode BatchNorm (what inference /
+    batch_with_preds uses) and train-mode BatchNorm.  The bf16 figures equal what PyTorch's own bf16 autocast shows
+    against fp32 on this network (same test, profiles/r02_parity512.json): they are the price of bf16 storage, not
+    of this implementation; the fp32 mode carries the 1e-4 mask claim."""
     from starcop_b200 import synthetic
     from starcop_b200.model_setup import get_model
     from starcop_b200.settings import default_settings
@@ -184,13 +187,18 @@ def mode_parity(dev, S):
         with torch.no_grad():
             lg = m(b["input"])
             loss = m.training_step(b, 1)
-        res[mode] = (torch.sigmoid(lg), float(loss))
+            m.eval()
+            le = m(b["input"])
+        res[mode] = (torch.sigmoid(lg), float(loss), torch.sigmoid(le))
         del m
-    d = (res["bf16"][0] - res["f32"][0]).abs()
-    return {"what": f"bf16 tcgen05 mode vs fp32 parity mode, 2 tiles {S}x{S}, train-mode BN, same weights",
-            "sigmoid_max_abs": d.max().item(), "sigmoid_mean_abs": d.mean().item(),
+    d, de = (res["bf16"][0] - res["f32"][0]).abs(), (res["bf16"][2] - res["f32"][2]).abs()
+    return {"what": f"bf16 tcgen05 mode vs fp32 parity mode, 2 tiles {S}x{S}, same weights",
+            "eval_bn_sigmoid_max_abs": de.max().item(), "eval_bn_sigmoid_mean_abs": de.mean().item(),
+            "train_bn_sigmoid_max_abs": d.max().item(), "train_bn_sigmoid_mean_abs": d.mean().item(),
             "loss_rel": abs(res["bf16"][1] - res["f32"][1]) / abs(res["f32"][1]),
-            "fp32_mode_vs_oracle": "<= 1e-4 sigmoid max-abs, 1e-5 loss (tests/test_gpu_parity512.py)"}
+            "fp32_mode_vs_oracle": "eval-mode sigmoid maps <= 1e-4 max-abs (measured 4e-7), loss 1e-5 (tests/test_gpu_parity512.py)",
+            "bf16_note": "train-mode BN at initialisation amplifies bf16 rounding (near-constant channels / tiny batch std): "
+                         "PyTorch bf16 autocast is equally far from fp32 (tests assert ours <= 1.3x autocast)"}
 
 
 def step_roofline(model, batch, pk):

@@ -174,14 +174,14 @@ int sc_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, co
  * x[pix*pixel_stride + s] for the S window bands (the caller offsets x to the first window band);
  * element type float (AVIRIS, process_aviris.py:199) or double (EMIT, mag1c_emit.py:46) per `fp64`.
  * pix_idx: (G, pmax) int32 pixel indices of each group, counts: G valid lengths (NULL = all pmax).
- * Groups with <= 10 pixels are skipped (mag1c.py:166): their outputs keep the caller's pre-fill
- * (-9999).  tmpl: S doubles.  mf_out / albedo_out: per-pixel outputs indexed by `pix` (scatter).
+ * Groups with <= skip_le pixels are skipped and their outputs keep the caller's pre-fill (-9999): func_by_groups
+ * passes 10 (mag1c.py:166), mag1c_emit processes every group that has a valid pixel (mag1c_emit.py:66-68).  tmpl: S doubles.  mf_out / albedo_out: per-pixel outputs indexed by `pix` (scatter).
  * num_iter = 0 is the plain matched filter `rmf`; alpha = diagonal loading (mag1c.py:246).
  * status: optional device int, incremented per group whose covariance was not positive definite. */
 int64_t sc_mag1c_smem_bytes(int S, int pmax, int elem_bytes);   /* must be <= 220 KB */
 int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_t* pix_idx, const int32_t* counts,
                     int pmax, const double* tmpl, void* mf_out, void* albedo_out, int G, int S,
-                    int num_iter, double alpha, int fp64, int* status, void* stream);
+                    int num_iter, double alpha, int fp64, int skip_le, int* status, void* stream);
 
 /* ---- A11/A13: band ratio product (starcop/data/feature_extration.py:32-56) ------------------
  * per tile: exact 5/95 percentiles (np.percentile linear) of each band by radix select, inlier
@@ -208,6 +208,30 @@ int sc_emit_rescale(const float* magic, const float* rgb, float* out, int H, int
 /* ---- A14: binary opening with the 3x3 cross (starcop/baselines.py:25-27, 54-58) ------------- */
 int sc_threshold_opening(const float* pred, float threshold, int64_t* out, uint8_t* scratch,
                          int B, int H, int W, void* stream);
+
+/* ---- (f)3: sensor simulation by spectral response functions (starcop/data/aviris.py:262-338, product at :324-326)
+ * over a BIP cube: out[k][p] = sum_c weights[k][c] * cube[p][c] (only where weights != 0), `fill` where any band
+ * with a non-zero weight equals `fill` (the reference's missing_values rule).  cube: n_pixels x C f32 (any
+ * 4-byte aligned address inside a device allocation), weights: K x C f32 device table (K <= 16; build it with the host recipe of aviris.py:275-316), out:
+ * K x n_pixels planar (the reference's (K,H,W)).  band_ranges_host: 2K ints on the HOST, [c0, c1) = the bands
+ * output band k touches (an SRF is a contiguous window), or NULL = all bands.  One pass: n_pixels * (C + K) * 4
+ * algorithmic bytes. */
+int sc_srf_aggregate(const float* cube_bip, int64_t n_pixels, int C, const float* weights,
+                     const int32_t* band_ranges_host, int K, float fill, float* out_planar, void* stream);
+
+/* ---- (f)1: training augmentation on the device (starcop/data/datamodule.py:128-134, kornia RandomRotation(p=.5,
+ * degrees=90) + RandomHorizontalFlip + RandomVerticalFlip applied jointly to input / label / loss weight): the
+ * composite is one affine resampling per sample.  in/out: (B,C,H,W) f32, distinct buffers; mats: B x 6 floats mapping
+ * OUTPUT pixel (x,y) to the source position (m0 x + m1 y + m2, m3 x + m4 y + m5), pixel centres at integers;
+ * bilinear (ATen grid_sampler weights) or nearest (nearbyint), zeros outside the image. */
+int sc_affine_warp(const float* in, float* out, const float* mats_dst_to_src, int B, int C, int H, int W,
+                   int nearest, void* stream);
+
+/* ---- A7: threshold sweep of run_validation (starcop/validation.py:37-42, 118-125) in one pass.  thresholds: K <= 64
+ * floats, ASCENDING (device).  hist: int64 [2][K+1], accumulated: hist[t][i] = pixels with y.long() == t whose
+ * prediction is > exactly i thresholds; the confusion matrix of threshold k follows by prefix sums (exact). */
+int sc_threshold_sweep(const float* pred, const float* y, const float* thresholds_ascending, int K, int64_t n,
+                       int64_t* hist, void* stream);
 
 /* ---- tcgen05 tensor-core path (bf16 storage, fp32 accumulate in TMEM) -----------------------
  * Implicit-GEMM convolution: A = activation tile fetched by TMA (shifted box per filter tap, zero

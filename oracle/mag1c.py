@@ -97,3 +97,28 @@ def mag1c_tile_columns(cube_bip, template, band_slice, num_iter=30, alpha=0.):
     x = torch.as_tensor(np.ascontiguousarray(cube_bip[:, :, band_slice])).permute(1, 0, 2).contiguous()
     mf, R = acrwl1mf(x, torch.as_tensor(template, dtype=x.dtype), num_iter=num_iter, alpha=alpha)
     return mf[..., 0].T.contiguous(), R[..., 0].T.contiguous()                  # (H, W) each
+
+
+@torch.no_grad()
+def mag1c_emit(raw_data, wavelengths, template, fill_value_default=-9999.0, use_wavelength_range=(2122, 2488),
+               num_iter=30, covariance_lerp_alpha=1e-4, column_step=None):
+    """starcop/models/mag1c_emit.py:40-90 with georreferenced=False; raw_data: (rows, cols, bands) numpy;
+    template: unit absorption spectrum of the SELECTED bands (the reference builds it at :45)."""
+    wl = np.asarray(wavelengths)
+    sel = (wl >= use_wavelength_range[0]) & (wl <= use_wavelength_range[1])                  # :40
+    raw = np.asarray(raw_data)[..., sel]
+    spec = torch.as_tensor(np.asarray(template, dtype=np.float64))
+    invalid = np.any(raw == fill_value_default, axis=-1)                                     # :51
+    mf_out = np.full(invalid.shape, dtype=np.float64, fill_value=fill_value_default)
+    al_out = np.full(invalid.shape, dtype=np.float64, fill_value=fill_value_default)
+    column_step = column_step or raw.shape[1]
+    for c0 in range(0, raw.shape[1], column_step):                                           # :58-84
+        c1 = min(c0 + column_step, raw.shape[1])
+        valid = ~invalid[:, c0:c1]
+        if not valid.any():
+            continue
+        x = torch.tensor(raw[:, c0:c1, :][valid, :][np.newaxis].astype(np.float64))
+        mf, al = acrwl1mf(x, spec, num_iter=num_iter, alpha=covariance_lerp_alpha)
+        mf_out[:, c0:c1][valid] = np.array(mf)[0, :, 0]
+        al_out[:, c0:c1][valid] = np.array(al)[0, :, 0]
+    return mf_out.astype(np.float32), al_out.astype(np.float32)

@@ -43,7 +43,7 @@ SIGNATURES = {
     "sc_adam_step": [P, P, P, P, L, F, F, F, F, I, F, P],
     "sc_adam_step_dev": [P, P, P, P, L, P, F, F, F, P, F, P],
     "sc_mag1c_smem_bytes": [I, I, I],
-    "sc_mag1c_filter": [P, L, P, P, I, P, P, P, I, I, I, D, I, P, P],
+    "sc_mag1c_filter": [P, L, P, P, I, P, P, P, I, I, I, D, I, I, P, P],
     "sc_ratio_workspace_bytes": [I, L],
     "sc_ratio_product": [P, P, P, I, L, F, F, P, P],
     "sc_weight_mag1c": [P, P, L, P],
@@ -52,6 +52,9 @@ SIGNATURES = {
     "sc_zero_override": [P, P, L, F, P],
     "sc_emit_rescale": [P, P, P, I, I, P],
     "sc_threshold_opening": [P, F, P, P, I, I, I, P],
+    "sc_threshold_sweep": [P, P, P, I, L, P, P],
+    "sc_affine_warp": [P, P, P, I, I, I, I, I, P],
+    "sc_srf_aggregate": [P, L, I, P, P, I, F, P, P],
     "sc_tc_supported": [],
     "sc_tc_pack_weights": [P, P, I, I, I, I, I, I, I, P],
     "sc_tc_pack_weights_batch": [P, I, L, P],

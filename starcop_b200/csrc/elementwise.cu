@@ -1025,3 +1025,89 @@ extern "C" int sc_threshold_opening(const float* pred, float threshold, int64_t*
   dilate_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(scratch, (long long*)out, B, H, W);
   return check_launch();
 }
+
+// ------------------------------------------------------------------------------------------------
+// A7: the precision / recall threshold sweep of run_validation (starcop/validation.py:37-42, 118-125) in ONE pass:
+// for K ascending thresholds, hist[t][i] counts the pixels of class t (= y.long()) whose prediction exceeds exactly
+// i of the thresholds (pred > thr_k, strict, like the reference); the confusion matrix of threshold k is then
+// [[sum_{i<=k} hist[0][i], sum_{i>k} hist[0][i]], [sum_{i<=k} hist[1][i], sum_{i>k} hist[1][i]]].  Integer
+// counts: exact.
+// ------------------------------------------------------------------------------------------------
+constexpr int kSweepMaxK = 64;
+__global__ void threshold_sweep_kernel(const float* __restrict__ pred, const float* __restrict__ y,
+                                       const float* __restrict__ thr, int K, int64_t n, unsigned long long* __restrict__ hist) {
+  __shared__ float s_thr[kSweepMaxK];
+  __shared__ unsigned int s_h[2 * (kSweepMaxK + 1)];
+  for (int i = threadIdx.x; i < K; i += blockDim.x) s_thr[i] = thr[i];
+  for (int i = threadIdx.x; i < 2 * (K + 1); i += blockDim.x) s_h[i] = 0u;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p = pred[i];
+    const int t = (int)(long long)y[i];
+    if (t != 0 && t != 1) continue;
+    int lo = 0, hi = K;                       // number of thresholds below p: first k with !(p > thr[k])
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (p > s_thr[mid]) lo = mid + 1; else hi = mid;
+    }
+    atomicAdd(&s_h[t * (K + 1) + lo], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * (K + 1); i += blockDim.x)
+    if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
+}
+
+extern "C" int sc_threshold_sweep(const float* pred, const float* y, const float* thresholds_ascending, int K, int64_t n,
+                                  int64_t* hist, void* stream) {
+  if (!pred || !y || !thresholds_ascending || !hist || K < 1 || K > kSweepMaxK || n <= 0) return SC_ERR_BAD_ARG;
+  int64_t blocks = (n + 4095) / 4096;
+  if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
+  threshold_sweep_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pred, y, thresholds_ascending, K, n,
+                                                                        (unsigned long long*)hist);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Training augmentation on the device (starcop/data/datamodule.py:128-134: kornia RandomRotation(p=.5, degrees=90)
+// + RandomHorizontalFlip + RandomVerticalFlip, applied jointly to input / label / loss weight).  The composite of
+// the three operators is ONE affine resampling per sample: out[b,c,y,x] = bilinear (or nearest) sample of in[b,c]
+// at (sx, sy) = (m0*x + m1*y + m2, m3*x + m4*y + m5), pixel centres at integer coordinates (align_corners=True),
+// zero outside the image -- kornia.warp_affine -> F.grid_sample(padding_mode="zeros") semantics.
+// ------------------------------------------------------------------------------------------------
+__global__ void affine_warp_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ mats,
+                                   int C, int H, int W, int nearest, int64_t total) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W);
+    int64_t t = i / W;
+    const int y = (int)(t % H);
+    t /= H;
+    const int c = (int)(t % C);
+    const int b = (int)(t / C);
+    const float* m = mats + b * 6;
+    const float sx = fmaf(m[0], (float)x, fmaf(m[1], (float)y, m[2]));
+    const float sy = fmaf(m[3], (float)x, fmaf(m[4], (float)y, m[5]));
+    const float* src = in + ((int64_t)b * C + c) * H * W;
+    float v = 0.f;
+    if (nearest) {
+      const int xi = (int)nearbyintf(sx), yi = (int)nearbyintf(sy);
+      if (xi >= 0 && xi < W && yi >= 0 && yi < H) v = src[(int64_t)yi * W + xi];
+    } else {
+      const float fx = floorf(sx), fy = floorf(sy);
+      const int x0 = (int)fx, y0 = (int)fy;
+      const float ax = sx - fx, ay = sy - fy;
+      auto at = [&](int yy, int xx) { return (xx >= 0 && xx < W && yy >= 0 && yy < H) ? src[(int64_t)yy * W + xx] : 0.f; };
+      // ATen grid_sampler_2d bilinear: nw*(1-ax)(1-ay) + ne*ax(1-ay) + sw*(1-ax)ay + se*ax*ay
+      v = at(y0, x0) * ((1.f - ax) * (1.f - ay)) + at(y0, x0 + 1) * (ax * (1.f - ay)) + at(y0 + 1, x0) * ((1.f - ax) * ay) +
+          at(y0 + 1, x0 + 1) * (ax * ay);
+    }
+    out[i] = v;
+  }
+}
+
+extern "C" int sc_affine_warp(const float* in, float* out, const float* mats_dst_to_src, int B, int C, int H, int W,
+                              int nearest, void* stream) {
+  if (!in || !out || !mats_dst_to_src || B <= 0 || C <= 0 || H <= 0 || W <= 0 || in == out) return SC_ERR_BAD_ARG;
+  const int64_t total = (int64_t)B * C * H * W;
+  affine_warp_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(in, out, mats_dst_to_src, C, H, W, nearest, total);
+  return check_launch();
+}

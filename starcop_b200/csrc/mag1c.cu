@@ -105,11 +105,11 @@ template <typename TS>
 __global__ void __launch_bounds__(kThreads)
 mag1c_kernel(const TS* __restrict__ x, int64_t pixel_stride, const int32_t* __restrict__ pix_idx,
              const int32_t* __restrict__ counts, int pmax, const double* __restrict__ tmpl, TS* __restrict__ mf_out,
-             TS* __restrict__ al_out, int S, int num_iter, double alpha, int* __restrict__ status) {
+             TS* __restrict__ al_out, int S, int num_iter, double alpha, int skip_le, int* __restrict__ status) {
   extern __shared__ double smd[];
   const int g = blockIdx.x;
   const int P = counts ? counts[g] : pmax;
-  if (P <= 10) return;                                 // mag1c.py:166-168: too few pixels, outputs stay NODATA
+  if (P <= skip_le) return;                            // mag1c.py:166-168 (skip_le = 10): too few pixels, outputs keep the pre-fill
   const int32_t* idx = pix_idx + (int64_t)g * pmax;
   const int NT = S * (S + 1) / 2;
   const int LD = mag1c_ld(S);
@@ -356,12 +356,12 @@ __host__ __device__ inline size_t res_smem_bytes(int S) {
 __global__ void __launch_bounds__(kResThreads, 1)
 mag1c_resident_kernel(const float* __restrict__ x, int64_t pixel_stride, const int32_t* __restrict__ pix_idx,
                       const int32_t* __restrict__ counts, int pmax, const double* __restrict__ tmpl,
-                      float* __restrict__ mf_out, float* __restrict__ al_out, int S, int num_iter,
+                      float* __restrict__ mf_out, float* __restrict__ al_out, int S, int num_iter, int skip_le,
                       int* __restrict__ status) {
   extern __shared__ double smd[];
   const int g = blockIdx.x;
   const int P = counts ? counts[g] : pmax;
-  if (P <= 10) return;                                 // mag1c.py:166-168: too few pixels, outputs stay NODATA
+  if (P <= skip_le) return;                            // mag1c.py:166-168 (skip_le = 10): too few pixels, outputs keep the pre-fill
   const int32_t* idx = pix_idx + (int64_t)g * pmax;
   const int SP = res_sp(S), LDA = res_lda(S);
   double* A = smd;                       // S x LDA: C0, then P0 = C0^-1
@@ -701,7 +701,8 @@ extern "C" int64_t sc_mag1c_smem_bytes(int S, int pmax, int elem_bytes) {
 
 extern "C" int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_t* pix_idx, const int32_t* counts,
                                int pmax, const double* tmpl, void* mf_out, void* albedo_out, int G, int S,
-                               int num_iter, double alpha, int fp64, int* status, void* stream) {
+                               int num_iter, double alpha, int fp64, int skip_le, int* status, void* stream) {
+  if (skip_le < 1) skip_le = 1;                        // a single pixel has no covariance
   if (!x || !pix_idx || !tmpl || !mf_out || !albedo_out || G <= 0 || S < 2 || S + 1 > kThreads || pmax < 1 || num_iter < 0)
     return SC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
@@ -712,7 +713,7 @@ extern "C" int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_
     e = cudaFuncSetAttribute(mag1c_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
     if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
     mag1c_resident_kernel<<<G, kResThreads, rs, st>>>((const float*)x, pixel_stride, pix_idx, counts, pmax, tmpl,
-                                                      (float*)mf_out, (float*)albedo_out, S, num_iter, status);
+                                                      (float*)mf_out, (float*)albedo_out, S, num_iter, skip_le, status);
     return check_launch();
   }
   size_t smem = (size_t)sc_mag1c_smem_bytes(S, pmax, fp64 ? 8 : 4);
@@ -721,12 +722,12 @@ extern "C" int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_
     e = cudaFuncSetAttribute(mag1c_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
     mag1c_kernel<double><<<G, kThreads, smem, st>>>((const double*)x, pixel_stride, pix_idx, counts, pmax, tmpl,
-                                                    (double*)mf_out, (double*)albedo_out, S, num_iter, alpha, status);
+                                                    (double*)mf_out, (double*)albedo_out, S, num_iter, alpha, skip_le, status);
   } else {
     e = cudaFuncSetAttribute(mag1c_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
     mag1c_kernel<float><<<G, kThreads, smem, st>>>((const float*)x, pixel_stride, pix_idx, counts, pmax, tmpl,
-                                                   (float*)mf_out, (float*)albedo_out, S, num_iter, alpha, status);
+                                                   (float*)mf_out, (float*)albedo_out, S, num_iter, alpha, skip_le, status);
   }
   return check_launch();
 }

@@ -1,0 +1,123 @@
+// Per-pixel spectral products over BIP hyperspectral cubes (the layout process_aviris.py:183-184 opens): every
+// pixel's spectrum is read from HBM exactly once and a handful of values per pixel are written.  These kernels are
+// bandwidth-bound by construction -- algorithmic bytes = pixels x (C_in + C_out) x 4 -- and are the
+// "spectral-product kernel" whose achieved HBM GB/s bench.py reports against the measured peak.
+//
+// sc_srf_aggregate: sensor simulation by spectral response functions (starcop/data/aviris.py:262-338, the product at
+// :324-326): out[k] = sum_c w[k][c] * x[c] over the bands the SRF of output band k touches, fill where any of those
+// bands is nodata.  A CTA streams chunks of pixels (a multiple of 4, so that every chunk is a 16-byte aligned,
+// 16-byte multiple run of the flat cube) through a ring of 1-D bulk copies (cp.async.bulk + mbarrier, three chunks
+// in flight per CTA), so the bytes in flight live in shared memory, not in registers; thread = (pixel of the chunk,
+// group of output bands) reads its pixel's spectrum from shared memory (pixel pitch = C floats: odd pitches are
+// conflict-free) against weights staged once per CTA.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace sc;
+
+namespace {
+
+constexpr int kSrfThreads = 256;
+constexpr int kSrfStages = 3;
+constexpr int kSrfMaxK = 16;
+
+struct SrfRanges {
+  int c0[kSrfMaxK], c1[kSrfMaxK];     // band range [c0, c1) with non-zero weight per output band
+};
+
+__global__ void __launch_bounds__(kSrfThreads, 2)
+srf_aggregate_kernel(const float* __restrict__ cube, int mis, int64_t n_pixels, int C, int ppc, const float* __restrict__ w,
+                     SrfRanges rg, int K, float fill, float* __restrict__ out) {
+  // cube is 4-byte aligned; `mis` floats precede it back to the previous 16-byte boundary (they belong to the same
+  // allocation: device allocations are 256-byte aligned).  Every chunk is fetched from that boundary: chunk c
+  // covers floats [c*ppc*C - mis, ...) of the cube, and a pixel's spectrum sits `mis` floats into its slot.
+  extern __shared__ __align__(128) uint8_t ssm[];
+  const uint32_t chunk_bytes = (uint32_t)ppc * C * 4 + 16;
+  const uint32_t chunk_pitch = (chunk_bytes + 127) & ~127u;
+  float* bufs = reinterpret_cast<float*>(ssm);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ssm + (size_t)kSrfStages * chunk_pitch);
+  float* sw = reinterpret_cast<float*>(full + kSrfStages + (kSrfStages & 1));        // [K][C] weights
+  const int tid = threadIdx.x;
+  const int64_t nchunks = (n_pixels + ppc - 1) / ppc;
+  const int64_t my_n = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+    for (int i = 0; i < kSrfStages; ++i) tc::mbar_init(&full[i], 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < K * C; i += kSrfThreads) sw[i] = w[i];
+  __syncthreads();
+  auto issue = [&](int64_t i) {
+    const int64_t p0 = (blockIdx.x + i * gridDim.x) * (int64_t)ppc;
+    const int64_t np = n_pixels - p0 < ppc ? n_pixels - p0 : ppc;
+    uint32_t bytes = (uint32_t)((np * C + mis) * 4);
+    bytes &= ~15u;                                     // a tail of < 16 bytes (cube size not a 16-byte multiple) is
+    const int slot = (int)(i % kSrfStages);            //   read straight from global memory below
+    tc::mbar_arrive_expect_tx(&full[slot], bytes);
+    tc::bulk_load_1d(reinterpret_cast<uint8_t*>(bufs) + (size_t)slot * chunk_pitch, cube + p0 * C - mis, bytes, &full[slot]);
+  };
+  if (tid == 0)
+    for (int i = 0; i < kSrfStages && i < my_n; ++i) issue(i);
+  const int ngroups = kSrfThreads / ppc;               // >= 1: the launcher keeps ppc <= 256
+  const int px = tid % ppc, kg = tid / ppc;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t i = 0; i < my_n; ++i) {
+    const int64_t p0 = (blockIdx.x + i * gridDim.x) * (int64_t)ppc;
+    const float* b = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(bufs) + (size_t)slot * chunk_pitch);
+    tc::mbar_wait(&full[slot], phase);
+    const int64_t p = p0 + px;
+    if (kg < ngroups && p < n_pixels) {
+      const float* xp = b + (size_t)px * C + mis;
+      const int64_t valid_floats = ((((n_pixels - p0 < ppc ? n_pixels - p0 : ppc) * C + mis) * 4) & ~15ll) / 4;
+      for (int k = kg; k < K; k += ngroups) {
+        const float* wk = sw + k * C;
+        float acc = 0.f;
+        bool miss = false;
+        for (int c = rg.c0[k]; c < rg.c1[k]; ++c) {
+          const int64_t off = (int64_t)px * C + c + mis;
+          const float v = off < valid_floats ? xp[c] : cube[p * C + c];
+          const float wv = wk[c];
+          if (wv != 0.f) {
+            miss |= v == fill;
+            acc = fmaf(wv, v, acc);
+          }
+        }
+        out[(int64_t)k * n_pixels + p] = miss ? fill : acc;
+      }
+    }
+    __syncthreads();                                   // every reader of the slot is done
+    if (tid == 0 && i + kSrfStages < my_n) issue(i + kSrfStages);
+    if (++slot == kSrfStages) {
+      slot = 0;
+      phase ^= 1;
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int sc_srf_aggregate(const float* cube_bip, int64_t n_pixels, int C, const float* weights,
+                                const int32_t* band_ranges_host, int K, float fill, float* out_planar, void* stream) {
+  if (!cube_bip || !weights || !out_planar || n_pixels <= 0 || C < 1 || K < 1 || K > kSrfMaxK) return SC_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(cube_bip) & 3) return SC_ERR_BAD_ARG;
+  const int mis = (int)((reinterpret_cast<uintptr_t>(cube_bip) & 15) / 4);
+  // pixels per chunk: a multiple of 4 (16-byte multiple runs for any C), <= 256 threads, <= 32 KB
+  int ppc = (32 * 1024) / (C * 4) / 4 * 4;
+  if (ppc > 256) ppc = 256;
+  if (ppc < 4) return SC_ERR_UNSUPPORTED;              // spectra longer than 2048 bands
+  cudaStream_t st = (cudaStream_t)stream;
+  SrfRanges rg;
+  for (int k = 0; k < K; ++k) {
+    rg.c0[k] = band_ranges_host ? band_ranges_host[2 * k] : 0;
+    rg.c1[k] = band_ranges_host ? band_ranges_host[2 * k + 1] : C;
+    if (rg.c0[k] < 0 || rg.c1[k] > C || rg.c0[k] > rg.c1[k]) return SC_ERR_BAD_ARG;
+  }
+  const size_t chunk_pitch = ((size_t)ppc * C * 4 + 16 + 127) & ~(size_t)127;
+  const size_t smem = kSrfStages * chunk_pitch + 64 + (size_t)K * C * 4;
+  cudaError_t e = cudaFuncSetAttribute(srf_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
+  const int64_t nchunks = (n_pixels + ppc - 1) / ppc;
+  const int grid = (int)(nchunks < 2 * kNumSMs ? nchunks : 2 * kNumSMs);
+  srf_aggregate_kernel<<<grid, kSrfThreads, smem, st>>>(cube_bip, mis, n_pixels, C, ppc, weights, rg, K, fill, out_planar);
+  return check_launch();
+}

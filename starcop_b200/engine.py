@@ -279,6 +279,9 @@ class UNetEngine:
                 off += buf.numel()
             host = torch.from_numpy(desc.view(np.uint8).copy()).pin_memory()      # pinned: the copy is legal even under capture
             self._pack_table = (host.to(self.device, non_blocking=True), len(self._packs), off, host)
+            # a CUDA graph captured earlier replays the batched re-pack with the table it saw: tables are never
+            # freed (a later, longer table only ADDS jobs -- new input sizes make more layers tensor-core eligible)
+            self._pack_tables_alive = getattr(self, "_pack_tables_alive", []) + [self._pack_table]
 
     def _halo_ok(self, x, cin, cout, k, stride):
         """thin 3x3 layers (decoder blocks 2-4): one staged halo patch per tile + resident weights (conv_tc_halo.cu)"""

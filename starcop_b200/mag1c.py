@@ -96,7 +96,7 @@ def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def _filter(x_flat, pixel_stride, pix_idx, counts, template, mf_out, al_out, S, num_iter, alpha):
+def _filter(x_flat, pixel_stride, pix_idx, counts, template, mf_out, al_out, S, num_iter, alpha, skip_le=10):
     dev = x_flat.device
     fp64 = x_flat.dtype == torch.float64
     tmpl = torch.as_tensor(np.asarray(template, dtype=np.float64) if not torch.is_tensor(template)
@@ -105,7 +105,7 @@ def _filter(x_flat, pixel_stride, pix_idx, counts, template, mf_out, al_out, S, 
     G, pmax = pix_idx.shape
     _lib.call("sc_mag1c_filter", x_flat.data_ptr(), pixel_stride, pix_idx.data_ptr(),
               counts.data_ptr() if counts is not None else 0, pmax, tmpl.data_ptr(), mf_out.data_ptr(),
-              al_out.data_ptr(), G, S, num_iter, float(alpha), int(fp64), status.data_ptr(), _stream(dev))
+              al_out.data_ptr(), G, S, num_iter, float(alpha), int(fp64), int(skip_le), status.data_ptr(), _stream(dev))
     return status
 
 
@@ -198,3 +198,61 @@ def mag1c_tiles(cube, template, band_slice, num_iter=30, alpha=0.):
     xw = cube.view(-1)[band_slice.start:]          # same storage, offset to the first window band
     _filter(xw, C, idx, None, template, mf, al, S, num_iter, alpha)
     return mf, al
+
+
+DEFAULT_WAVELENGTH_RANGE = (2122, 2488)
+
+
+@torch.no_grad()
+def mag1c_emit(raw_data, wavelengths, template=None, fwhm=None, fill_value_default=-9999.0,
+               use_wavelength_range=DEFAULT_WAVELENGTH_RANGE, num_iter=30, covariance_lerp_alpha=1e-4, column_step=None,
+               lut_dir=None, check=True):
+    """``starcop.models.mag1c_emit.mag1c_emit`` (mag1c_emit.py:16-90) on a raw (rows, cols, bands) EMIT cube that is
+    already on the GPU (the georeader ``EMITImage`` container and the geo-referencing of the result are out of
+    scope: this is the ``georreferenced=False`` path the inference notebook uses).
+
+    Bands with ``lo <= wavelength <= hi`` are selected (:40), pixels with any selected band equal to the fill value
+    are invalid (:51), the cube is processed in float64 (:75) in groups of ``column_step`` detector columns (:56-84;
+    every group with at least one valid pixel is filtered: there is no <= 10 pixel rule here), with diagonal
+    loading ``alpha = 1e-4`` (:18).  ``template``: the unit absorption spectrum of the SELECTED bands, or None to
+    build it from ``fwhm`` with ``generate_template_from_bands`` (:45).  Returns (mf, albedo), each (rows, cols)
+    float32 with the fill value where nothing was computed (:90)."""
+    if not raw_data.is_cuda:
+        raise _lib.StarcopB200Error("starcop_b200 runs on CUDA tensors only (no CPU path)")
+    wl = np.asarray(wavelengths, dtype=np.float64)
+    sel = (wl >= use_wavelength_range[0]) & (wl <= use_wavelength_range[1])
+    assert sel.any(), "There are no bands in the selected wavelength range"
+    idx = np.where(sel)[0]
+    if template is None:
+        assert fwhm is not None, "pass the template of the selected bands, or the bands' fwhm to build it"
+        template = generate_template_from_bands(wl[sel], np.asarray(fwhm, dtype=np.float64)[sel], lut_dir=lut_dir)[:, 1]
+    template = np.asarray(template, dtype=np.float64)
+    S = len(idx)
+    assert template.shape[0] == S, f"template has {template.shape[0]} bands, {S} selected"
+    rows, cols, _ = raw_data.shape
+    dev = raw_data.device
+    contiguous = bool(np.all(np.diff(idx) == 1))
+    x = (raw_data[..., int(idx[0]):int(idx[-1]) + 1] if contiguous else raw_data[..., torch.as_tensor(idx, device=dev)])
+    invalid = torch.any(x == fill_value_default, dim=-1)                                       # (rows, cols)
+    x64 = x.to(torch.float64).contiguous()                                                     # :75
+    column_step = column_step or cols
+    starts = list(range(0, cols, column_step))
+    G, pmax = len(starts), rows * column_step
+    # per group: the valid pixels of raw[:, c0:c1] in row-major order of the slice (``raw_data_slice[valid_slice]``)
+    valid = ~invalid
+    flat = torch.arange(rows * cols, device=dev, dtype=torch.int32).view(rows, cols)
+    pix = torch.zeros(G, pmax, dtype=torch.int32, device=dev)
+    cnt = torch.zeros(G, dtype=torch.int32, device=dev)
+    for g, c0 in enumerate(starts):                       # host loop over groups like the reference's; device-side gathers
+        c1 = min(c0 + column_step, cols)
+        v = valid[:, c0:c1]
+        ids = flat[:, c0:c1][v]
+        n = int(ids.numel())
+        pix[g, :n] = ids
+        cnt[g] = n
+    mf = torch.full((rows, cols), float(fill_value_default), dtype=torch.float64, device=dev)
+    al = torch.full((rows, cols), float(fill_value_default), dtype=torch.float64, device=dev)
+    status = _filter(x64, S, pix, cnt, template, mf, al, S, num_iter, covariance_lerp_alpha, skip_le=0)
+    if check and int(status.item()):
+        raise torch.linalg.LinAlgError(f"linalg.cholesky: covariance of {int(status.item())} group(s) is not positive-definite")
+    return mf.float(), al.float()

@@ -561,7 +561,10 @@ class ModelModule(_Base):
         ``step.prefetch(batch)``: the host-to-device copy of the NEXT batch runs on a copy stream while the
         current step computes (what a pinned-memory DataLoader + ``non_blocking`` transfer does in the
         reference loop); ``step()`` without arguments then consumes the oldest prefetched batch."""
-        assert warmup >= 1, "at least one eager step must run first (it sizes the arenas and caches host state)"
+        # at least one eager step at THIS batch shape must have run (it sizes the arenas, records the weight-packing
+        # plan and caches host state): either `warmup` >= 1 here, or the caller just ran train_step_fused on it
+        assert warmup >= 1 or (self.network._engine is not None and self.network._engine._plan_complete), \
+            "run one eager train_step_fused on this batch shape first, or pass warmup >= 1"
         dev = example_batch["input"].device
         keys = ["input", "output"] + (["weight_loss"] if self.reduction == "none" else [])
         nset = 2 if double_buffer else 1
