@@ -19,6 +19,7 @@ import sys
 import threading
 import time
 
+import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -254,7 +255,6 @@ def spectral_products_bench(dev, pk, tiles=8, size=512, bands=125, iters=5):
     """configs[2] front end: 125-band AVIRIS-shape BIP cubes -> mag1c matched filter (+ RGB pick) and the band
     ratio product, timed with CUDA events on resident inputs.  Algorithmic bytes: the whole cube read
     once + 4 output channels written = size*size*(bands+4)*4 per tile; ratio: 12 B / pixel."""
-    import numpy as np
     from starcop_b200 import features, mag1c, synthetic
     g = torch.Generator(device=dev).manual_seed(0)
     c = torch.arange(bands, device=dev, dtype=torch.float32)
@@ -291,7 +291,110 @@ def spectral_products_bench(dev, pk, tiles=8, size=512, bands=125, iters=5):
     gbs = tiles * size * size * 12 / sec / 1e9
     out["ratio_2c_outlier"] = {"tiles_per_s": tiles / sec, "us_per_tile": sec / tiles * 1e6, "achieved_gbs": gbs,
                                "frac_of_hbm_peak": gbs / pk["hbm_gbs"], "bound": "hbm (exact percentile select + apply)"}
+    # SRF band aggregation (aviris.py:262-338): the single-pass per-pixel spectral product -- every cube byte read once,
+    # 8 simulated bands written: algorithmic bytes = size*size*(bands + 8)*4 per tile
+    from starcop_b200 import srf
+    centers = 380.0 + 17.0 * np.arange(bands)
+    wl = np.arange(400.0, 2400.0, 2.0)
+    resp = np.stack([np.exp(-0.5 * ((wl - (450 + 230 * k)) / 40.0) ** 2) for k in range(8)])
+    Wt = srf.srf_weight_table(wl, resp, centers)
+    sec = timeit(lambda: srf.transform_to_srf(cube, Wt, 0.0))
+    gbs = tiles * size * size * (bands + 8) * 4 / sec / 1e9
+    out["srf_aggregate_8_bands"] = {"tiles_per_s": tiles / sec, "us_per_tile": sec / tiles * 1e6, "achieved_gbs": gbs,
+                                    "frac_of_hbm_peak": gbs / pk["hbm_gbs"], "bound": "hbm (one pass: cube read once, 8 bands written)"}
     out["workload"] = f"{tiles} cubes of {size}x{size}x{bands} f32 BIP, 73-band SWIR window, groups = detector columns"
+    return out
+
+
+def chain_bench(dev, pk, dtype, B=8, size=512, bands=125, steps=5):
+    """BASELINE.json configs[2]: bs=8 cubes of 512x512x125 -> mag1c (30 iterations, groups = detector columns) -> fused
+    pack (RGB pick + normalise + NHWC, weight_mag1c) -> U-Net train step (fwd + BCE + bwd + Adam), one timed chain
+    on resident cubes (4 x 131 MB cubes rotate so that no step finds its cube in L2)."""
+    from starcop_b200 import chain, synthetic
+    from starcop_b200.model_setup import get_model
+    from starcop_b200.settings import default_settings
+    torch.manual_seed(0)
+    model = get_model(default_settings(pos_weight=1.0, compute_dtype=dtype), None).to(dev).train()
+    g = torch.Generator(device=dev).manual_seed(0)
+    c = torch.arange(bands, device=dev, dtype=torch.float32)
+    mu = 8.0 * torch.exp(-c / (0.9 * bands)) + 0.6 + 0.15 * torch.sin(c * 0.37)
+    cubes = []
+    for _ in range(2):
+        albedo = torch.nn.functional.interpolate(torch.rand(B, 1, 9, 9, device=dev, generator=g) + 0.5, size=(size, size),
+                                                 mode="bilinear", align_corners=True)[:, 0]
+        cubes.append(albedo[..., None] * mu * (1.0 + 0.01 * torch.randn(B, size, size, bands, device=dev, generator=g)))
+    tmpl = synthetic.synthetic_template(73)
+    sl = slice(52, 125)
+    rgb = (40, 25, 10)
+    y = (torch.rand(B, 1, size, size, device=dev, generator=g) > 0.98).float()
+
+    def step(i):
+        b = chain.cube_batch(model, cubes[i % 2], tmpl, sl, rgb, output=y)
+        return model.train_step_fused(b)
+    for i in range(2):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    for i in range(steps):                                  # the filter stage alone, same cubes
+        chain.cube_batch(model, cubes[i % 2], tmpl, sl, rgb, output=y)
+    e2.record()
+    torch.cuda.synchronize()
+    ms, ms_f = e0.elapsed_time(e1) / steps, e1.elapsed_time(e2) / steps
+    cube_bytes = B * size * size * (bands + 4) * 4
+    return {"workload": f"configs[2]: {B} cubes of {size}x{size}x{bands} f32 BIP -> mag1c (acrwl1mf, 30 iterations) -> fused pack -> "
+                        f"U-Net train step, {dtype}", "tiles_per_s": B / (ms * 1e-3), "ms_per_step": ms,
+            "ms_spectral_stage": ms_f, "ms_unet_stage": ms - ms_f,
+            "spectral_stage_gbs": cube_bytes / (ms_f * 1e-3) / 1e9, "spectral_stage_frac_of_hbm_peak": cube_bytes / (ms_f * 1e-3) / 1e9 / pk["hbm_gbs"],
+            "steps": steps}
+
+
+def emit_sweep_bench(dev, pk, dtype, rows=1280, cols=1242, bands=285):
+    """BASELINE.json configs[4] on one GPU: an EMIT-shape granule (rows x cols x 285 f32 BIP) -> mag1c_emit (fp64,
+    621 two-column groups, alpha 1e-4, 30 iterations; mag1c_emit.py:16-90) -> RGB pick + EMIT rescale -> sigmoid(U-Net)
+    in eval mode, un-tiled (padded_predict, the notebook's call) and tiled at 256 / 512 / 1024 px."""
+    from starcop_b200 import emit, synthetic
+    from starcop_b200.model_setup import get_model
+    from starcop_b200.settings import default_settings
+    torch.manual_seed(0)
+    model = get_model(default_settings(pos_weight=1.0, compute_dtype=dtype), None).to(dev).eval()
+    g = torch.Generator(device=dev).manual_seed(1)
+    wl = np.linspace(381.0, 2493.0, bands)
+    c = torch.arange(bands, device=dev, dtype=torch.float32)
+    mu = 8.0 * torch.exp(-c / (0.9 * bands)) + 0.6
+    raw = (torch.rand(rows, cols, 1, device=dev, generator=g) + 0.5) * mu * (1.0 + 0.01 * torch.randn(rows, cols, bands, device=dev, generator=g))
+    S = int(((wl >= 2122) & (wl <= 2488)).sum())
+    tmpl = synthetic.synthetic_template(S)
+
+    def timeit(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    out = {"workload": f"configs[4] (one GPU): EMIT-shape granule {rows}x{cols}x{bands} f32 BIP, {S}-band window, fp64 matched filter in "
+                       f"{(cols + 1) // 2} two-column groups, eval-mode {dtype} U-Net"}
+    x = {}
+    ms_f = timeit(lambda: x.update(inp=emit.emit_model_input(raw, wl, template=tmpl, column_step=2)[0]), n=2)
+    cube_bytes = rows * cols * (bands + 4) * 4
+    out["mag1c_emit_fp64"] = {"ms": ms_f, "groups_per_s": ((cols + 1) // 2) / (ms_f * 1e-3), "cube_gbs": cube_bytes / (ms_f * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": cube_bytes / (ms_f * 1e-3) / 1e9 / pk["hbm_gbs"],
+                              "reference": "28 s on Colab CPU (21.8 groups/s), notebooks/inference_on_raw_EMIT_nc_file.ipynb:282"}
+    scene = x["inp"]
+    px = scene.shape[-1] * scene.shape[-2]
+    for tile in (None, 256, 512, 1024):
+        with torch.no_grad():
+            ms = timeit(lambda: emit.predict_scene(scene, model, tile=tile, batch=16))
+        out["unet_" + ("untiled" if tile is None else f"tile{tile}")] = {"ms": ms, "mpx_per_s": px / (ms * 1e-3) / 1e6,
+                                                                        "tiles512_equiv_per_s": px / (512 * 512) / (ms * 1e-3),
+                                                                        "fwd_tflops": px / (512 * 512) * UNET_FWD_GFLOP_PER_TILE / ms}
     return out
 
 
@@ -457,6 +560,18 @@ def main():
             spectral = spectral_products_bench(dev, pk)
         except Exception as e:          # noqa: BLE001  (reported, never silently dropped)
             spectral = {"error": repr(e)}
+    chain_res = emit_res = None
+    if rank == 0 and world == 1 and not args.no_spectral:
+        for name, fn in (("chain", lambda: chain_bench(dev, pk, args.dtype)), ("emit", lambda: emit_sweep_bench(dev, pk, args.dtype))):
+            try:
+                r = fn()
+            except Exception as e:          # noqa: BLE001
+                r = {"error": repr(e)[:300]}
+            if name == "chain":
+                chain_res = r
+            else:
+                emit_res = r
+            torch.cuda.empty_cache()
     eager = parity = None
     if rank == 0 and world == 1 and not args.no_extras:
         try:
@@ -488,6 +603,7 @@ def main():
             "roofline": roof, "roofline_summary": summary, "roofline_table": table,
             "largest_gemm_probe": probe,
             "cpu_baseline": cpu, "gpu_eager_baseline": eager, "parity": parity, "spectral_products": spectral,
+            "configs2_cube_to_unet_chain": chain_res, "configs4_emit_inference_sweep": emit_res,
         }
         emit(line)
     if world > 1:

@@ -213,11 +213,19 @@ int sc_threshold_opening(const float* pred, float threshold, int64_t* out, uint8
  * over a BIP cube: out[k][p] = sum_c weights[k][c] * cube[p][c] (only where weights != 0), `fill` where any band
  * with a non-zero weight equals `fill` (the reference's missing_values rule).  cube: n_pixels x C f32 (any
  * 4-byte aligned address inside a device allocation), weights: K x C f32 device table (K <= 16; build it with the host recipe of aviris.py:275-316), out:
- * K x n_pixels planar (the reference's (K,H,W)).  band_ranges_host: 2K ints on the HOST, [c0, c1) = the bands
+ * (n_pixels / tile_pixels) x K x tile_pixels planar (the reference's (K,H,W) for each of the stacked scenes).  band_ranges_host: 2K ints on the HOST, [c0, c1) = the bands
  * output band k touches (an SRF is a contiguous window), or NULL = all bands.  One pass: n_pixels * (C + K) * 4
  * algorithmic bytes. */
-int sc_srf_aggregate(const float* cube_bip, int64_t n_pixels, int C, const float* weights,
+int sc_srf_aggregate(const float* cube_bip, int64_t n_pixels, int64_t tile_pixels, int C, const float* weights,
                      const int32_t* band_ranges_host, int K, float fill, float* out_planar, void* stream);
+
+/* ---- configs[2] glue (process_aviris.py:183-219 -> dataset -> model_module.py:98): matched-filter output + the three
+ * cube bands of the RGB products -> the network's normalised NHWC input in one pass (what sc_normalize_pack makes of
+ * the NCHW batch [clip(mf,0,1e4), R, G, B]; integer normaliser factors only, i.e. the HyperSTARCOP products), and
+ * optionally the raw NCHW batch (B,4,H,W) and weight_mag1c = clip(mf/400, .1, 1) (feature_extration.py:32-35). */
+int sc_chain_pack(const float* mf, const float* cube_bip, int C, int band_r, int band_g, int band_b, const double* off,
+                  const double* fac, const double* lo, const double* hi, int B, int64_t HW, void* out_nhwc, int ld,
+                  int dtype, float* out_nchw, float* weight_loss, void* stream);
 
 /* ---- (f)1: training augmentation on the device (starcop/data/datamodule.py:128-134, kornia RandomRotation(p=.5,
  * degrees=90) + RandomHorizontalFlip + RandomVerticalFlip applied jointly to input / label / loss weight): the

@@ -54,7 +54,8 @@ SIGNATURES = {
     "sc_threshold_opening": [P, F, P, P, I, I, I, P],
     "sc_threshold_sweep": [P, P, P, I, L, P, P],
     "sc_affine_warp": [P, P, P, I, I, I, I, I, P],
-    "sc_srf_aggregate": [P, L, I, P, P, I, F, P, P],
+    "sc_srf_aggregate": [P, L, L, I, P, P, I, F, P, P],
+    "sc_chain_pack": [P, P, I, I, I, I, P, P, P, P, I, L, P, I, I, P, P, P],
     "sc_tc_supported": [],
     "sc_tc_pack_weights": [P, P, I, I, I, I, I, I, I, P],
     "sc_tc_pack_weights_batch": [P, I, L, P],

@@ -10,6 +10,8 @@
 // in flight per CTA), so the bytes in flight live in shared memory, not in registers; thread = (pixel of the chunk,
 // group of output bands) reads its pixel's spectrum from shared memory (pixel pitch = C floats: odd pitches are
 // conflict-free) against weights staged once per CTA.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -18,16 +20,19 @@ using namespace sc;
 namespace {
 
 constexpr int kSrfThreads = 256;
-constexpr int kSrfStages = 3;
+#ifndef SRF_STAGES
+#define SRF_STAGES 3
+#endif
+constexpr int kSrfStages = SRF_STAGES;
 constexpr int kSrfMaxK = 16;
 
 struct SrfRanges {
   int c0[kSrfMaxK], c1[kSrfMaxK];     // band range [c0, c1) with non-zero weight per output band
 };
 
-__global__ void __launch_bounds__(kSrfThreads, 2)
-srf_aggregate_kernel(const float* __restrict__ cube, int mis, int64_t n_pixels, int C, int ppc, const float* __restrict__ w,
-                     SrfRanges rg, int K, float fill, float* __restrict__ out) {
+__global__ void __launch_bounds__(kSrfThreads, 4)
+srf_aggregate_kernel(const float* __restrict__ cube, int mis, int64_t n_pixels, int64_t tile_pixels, int C, int ppc,
+                     const float* __restrict__ w, SrfRanges rg, int K, float fill, float* __restrict__ out, int dbg) {
   // cube is 4-byte aligned; `mis` floats precede it back to the previous 16-byte boundary (they belong to the same
   // allocation: device allocations are 256-byte aligned).  Every chunk is fetched from that boundary: chunk c
   // covers floats [c*ppc*C - mis, ...) of the cube, and a pixel's spectrum sits `mis` floats into its slot.
@@ -66,23 +71,36 @@ srf_aggregate_kernel(const float* __restrict__ cube, int mis, int64_t n_pixels, 
     const float* b = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(bufs) + (size_t)slot * chunk_pitch);
     tc::mbar_wait(&full[slot], phase);
     const int64_t p = p0 + px;
-    if (kg < ngroups && p < n_pixels) {
+    if (kg < ngroups && p < n_pixels && !(dbg & 1)) {
       const float* xp = b + (size_t)px * C + mis;
       const int64_t valid_floats = ((((n_pixels - p0 < ppc ? n_pixels - p0 : ppc) * C + mis) * 4) & ~15ll) / 4;
+      // only the very last pixels of a cube whose byte size is not a 16-byte multiple miss the staged tail
+      const bool staged = (int64_t)(px + 1) * C + mis <= valid_floats;
       for (int k = kg; k < K; k += ngroups) {
         const float* wk = sw + k * C;
         float acc = 0.f;
         bool miss = false;
-        for (int c = rg.c0[k]; c < rg.c1[k]; ++c) {
-          const int64_t off = (int64_t)px * C + c + mis;
-          const float v = off < valid_floats ? xp[c] : cube[p * C + c];
-          const float wv = wk[c];
-          if (wv != 0.f) {
-            miss |= v == fill;
-            acc = fmaf(wv, v, acc);
+        if (staged) {
+#pragma unroll 4
+          for (int c = rg.c0[k]; c < rg.c1[k]; ++c) {
+            const float v = xp[c], wv = wk[c];
+            miss |= (v == fill) & (wv != 0.f);
+            acc = fmaf(wv, v, acc);                      // a zero weight contributes exactly 0 (finite radiances)
+          }
+        } else {
+          for (int c = rg.c0[k]; c < rg.c1[k]; ++c) {
+            const int64_t off = (int64_t)px * C + c + mis;
+            const float v = off < valid_floats ? xp[c] : cube[p * C + c];
+            const float wv = wk[c];
+            if (wv != 0.f) {
+              miss |= v == fill;
+              acc = fmaf(wv, v, acc);
+            }
           }
         }
-        out[(int64_t)k * n_pixels + p] = miss ? fill : acc;
+        // planar per tile: (tile, K, tile_pixels) -- the reference's (K, H, W) for each scene
+        const int64_t t = p / tile_pixels, sp = p - t * tile_pixels;
+        out[(t * K + k) * tile_pixels + sp] = miss ? fill : acc;
       }
     }
     __syncthreads();                                   // every reader of the slot is done
@@ -96,13 +114,17 @@ srf_aggregate_kernel(const float* __restrict__ cube, int mis, int64_t n_pixels, 
 
 }  // namespace
 
-extern "C" int sc_srf_aggregate(const float* cube_bip, int64_t n_pixels, int C, const float* weights,
+extern "C" int sc_srf_aggregate(const float* cube_bip, int64_t n_pixels, int64_t tile_pixels, int C, const float* weights,
                                 const int32_t* band_ranges_host, int K, float fill, float* out_planar, void* stream) {
   if (!cube_bip || !weights || !out_planar || n_pixels <= 0 || C < 1 || K < 1 || K > kSrfMaxK) return SC_ERR_BAD_ARG;
+  if (tile_pixels <= 0 || n_pixels % tile_pixels) return SC_ERR_BAD_ARG;
   if (reinterpret_cast<uintptr_t>(cube_bip) & 3) return SC_ERR_BAD_ARG;
   const int mis = (int)((reinterpret_cast<uintptr_t>(cube_bip) & 15) / 4);
-  // pixels per chunk: a multiple of 4 (16-byte multiple runs for any C), <= 256 threads, <= 32 KB
-  int ppc = (32 * 1024) / (C * 4) / 4 * 4;
+  // pixels per chunk: a multiple of 4 (16-byte multiple runs for any C), <= 256 threads
+  // measured at 512 x 512 x 125 (bs 8): 16 KB chunks x 3 stages x 4 CTAs / SM = 5.1 TB/s (32 KB x 2 CTAs: 4.8; the
+  // copy ring alone, arithmetic skipped: 7.1 TB/s)
+  const int chunk_kb = getenv("STARCOP_SRF_KB") ? atoi(getenv("STARCOP_SRF_KB")) : 16;
+  int ppc = (chunk_kb * 1024) / (C * 4) / 4 * 4;
   if (ppc > 256) ppc = 256;
   if (ppc < 4) return SC_ERR_UNSUPPORTED;              // spectra longer than 2048 bands
   cudaStream_t st = (cudaStream_t)stream;
@@ -117,7 +139,61 @@ extern "C" int sc_srf_aggregate(const float* cube_bip, int64_t n_pixels, int C, 
   cudaError_t e = cudaFuncSetAttribute(srf_aggregate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
   const int64_t nchunks = (n_pixels + ppc - 1) / ppc;
-  const int grid = (int)(nchunks < 2 * kNumSMs ? nchunks : 2 * kNumSMs);
-  srf_aggregate_kernel<<<grid, kSrfThreads, smem, st>>>(cube_bip, mis, n_pixels, C, ppc, weights, rg, K, fill, out_planar);
+  const int ctas = getenv("STARCOP_SRF_CTAS") ? atoi(getenv("STARCOP_SRF_CTAS")) : 4;
+  const int grid = (int)(nchunks < ctas * kNumSMs ? nchunks : ctas * kNumSMs);
+  srf_aggregate_kernel<<<grid, kSrfThreads, smem, st>>>(cube_bip, mis, n_pixels, tile_pixels, C, ppc, weights, rg, K, fill, out_planar,
+                                                        getenv("STARCOP_SRF_DBG") ? atoi(getenv("STARCOP_SRF_DBG")) : 0);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
+// configs[2] glue: matched-filter output + three cube bands -> the network's input, in ONE pass.
+// For every pixel: ch0 = clip(mf, 0, 10000) (the cached-dataset clamp, sampling_dataset.py:292-293), ch1..3 = the
+// cube's bands nearest 640 / 550 / 460 nm (TOA_AVIRIS_*nm products), then DataNormalizer.normalize_x
+// (normalizer_module.py:134-135: IEEE division, clamp) and the NHWC pack at channel stride ld (channels >= 4 zero)
+// that sc_normalize_pack would produce from the NCHW batch -- plus, optionally, the raw NCHW batch itself ("input" of
+// the DataLoader contract) and weight_mag1c = clip(mf / 400, .1, 1) (feature_extration.py:32-35).
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void chain_pack_kernel(const float* __restrict__ mf, const float* __restrict__ cube, int C, int b0, int b1, int b2,
+                                  const double* __restrict__ off, const double* __restrict__ fac, const double* __restrict__ lo,
+                                  const double* __restrict__ hi, int64_t HW, int64_t total, T* __restrict__ out_nhwc, int ld,
+                                  float* __restrict__ out_nchw, float* __restrict__ weight) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total; p += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = p / HW, s = p - b * HW;
+    const float* px = cube + p * C;
+    float v[4];
+    const float m = mf[p];
+    v[0] = m < 0.f ? 0.f : (m > 10000.f ? 10000.f : m);
+    v[1] = px[b0];
+    v[2] = px[b1];
+    v[3] = px[b2];
+    if (weight) {
+      const float wv = v[0] / 400.f;
+      weight[p] = wv < 0.1f ? 0.1f : (wv > 1.f ? 1.f : wv);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (out_nchw) out_nchw[(b * 4 + c) * HW + s] = v[c];
+      const float d = (v[c] - (float)off[c]) / (float)fac[c];
+      const float l = (float)lo[c], h = (float)hi[c];
+      if (out_nhwc) out_nhwc[p * ld + c] = from_f<T>(d < l ? l : (d > h ? h : d));
+    }
+    if (out_nhwc)
+      for (int c = 4; c < ld; ++c) out_nhwc[p * ld + c] = from_f<T>(0.f);
+  }
+}
+
+extern "C" int sc_chain_pack(const float* mf, const float* cube_bip, int C, int band_r, int band_g, int band_b, const double* off,
+                             const double* fac, const double* lo, const double* hi, int B, int64_t HW, void* out_nhwc, int ld,
+                             int dtype, float* out_nchw, float* weight_loss, void* stream) {
+  if (!mf || !cube_bip || !off || !fac || !lo || !hi || B <= 0 || HW <= 0 || (out_nhwc && ld < 4)) return SC_ERR_BAD_ARG;
+  if (band_r < 0 || band_g < 0 || band_b < 0 || band_r >= C || band_g >= C || band_b >= C) return SC_ERR_BAD_ARG;
+  const int64_t total = (int64_t)B * HW;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  SC_DISPATCH_DTYPE(dtype, (chain_pack_kernel<T><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+                               mf, cube_bip, C, band_r, band_g, band_b, off, fac, lo, hi, HW, total, (T*)out_nhwc, ld, out_nchw,
+                               weight_loss)));
   return check_launch();
 }

@@ -113,28 +113,40 @@ class HyperStarcopUnet(UnetParameters):
 
     # ---- forward / backward -------------------------------------------------------------------
     def _forward_impl(self, x, norm, training, record=None):
+        """x: (B,C,H,W) tensor, or a producer ``(B, H, W, device, fill)`` whose ``fill(ptr, ld, dtype, stream)`` writes
+        the normalised NHWC input straight into the engine's input buffer (the spectral chain's fused pack)."""
         self._materialize()
         eng = self._engine
-        x = x.contiguous().float()
-        B, C, H, W = x.shape
+        producer = None
+        if isinstance(x, tuple):
+            B, H, W, dev_, producer = x
+            C = self.in_channels
+            x = None
+        else:
+            x = x.contiguous().float()
+            B, C, H, W = x.shape
+            dev_ = x.device
         assert C == self.in_channels, f"expected {self.in_channels} input channels, got {C}"
         if H % 32 or W % 32:                     # smp check_input_shape
             raise RuntimeError(f"Wrong input shape height={H}, width={W}. Expected image height and width "
                                f"divisible by 32.")
-        eng.stream = _stream(x.device)
+        eng.stream = _stream(dev_)
         eng.begin_step(record=training if record is None else record)
         ldin = C if eng.dtype == _lib.SC_F32 else (C + 7) // 8 * 8
         xin = eng.new(B, H, W, C, ld=ldin)
-        if norm is None:
-            prm, mask = self._identity_norm(x.device, C), 0
+        if producer is not None:
+            producer(xin.ptr, ldin, eng.dtype, eng.stream)
         else:
-            prm, mask = norm
-        _lib.call("sc_normalize_pack", x.data_ptr(), prm[0].data_ptr(), prm[1].data_ptr(), prm[2].data_ptr(),
-                  prm[3].data_ptr(), mask, B, C, H, W, xin.ptr, ldin, eng.dtype, 0, eng.stream)
-        logits = torch.empty(B, 1, H, W, dtype=torch.float32, device=x.device)
+            if norm is None:
+                prm, mask = self._identity_norm(dev_, C), 0
+            else:
+                prm, mask = norm
+            _lib.call("sc_normalize_pack", x.data_ptr(), prm[0].data_ptr(), prm[1].data_ptr(), prm[2].data_ptr(),
+                      prm[3].data_ptr(), mask, B, C, H, W, xin.ptr, ldin, eng.dtype, 0, eng.stream)
+        logits = torch.empty(B, 1, H, W, dtype=torch.float32, device=dev_)
         eng.forward(xin, logits.data_ptr(), training, record)
         if training:
-            if getattr(self, "_nbt", None) is None or self._nbt[0].device != x.device:
+            if getattr(self, "_nbt", None) is None or self._nbt[0].device != dev_:
                 self._nbt = [b for n, b in self.named_buffers() if n.endswith("num_batches_tracked")]
             torch._foreach_add_(self._nbt, 1)
         return logits
@@ -535,7 +547,8 @@ class ModelModule(_Base):
         x, y = batch["input"], batch["output"]
         w = batch["weight_loss"] if self.reduction == "none" else None
         net.train()
-        logits = net._forward_impl(x, self.normalizer.kernel_params(x.device), True)
+        # batch["input"] may be a producer tuple (spectral chain: the pack kernel writes the engine's input buffer)
+        logits = net._forward_impl(x, None if isinstance(x, tuple) else self.normalizer.kernel_params(x.device), True)
         B = logits.shape[0]
         n = logits.numel()
         dev = logits.device

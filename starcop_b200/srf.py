@@ -38,19 +38,32 @@ def transform_to_srf(cube_bip, weights, fill_value_default=0.0):
         raise _lib.StarcopB200Error("starcop_b200 runs on CUDA tensors only (no CPU path)")
     x = cube_bip.contiguous().float()
     *lead, H, W, C = x.shape
-    Wt = np.asarray(weights.detach().cpu() if torch.is_tensor(weights) else weights, dtype=np.float64)
-    K = Wt.shape[0]
-    assert Wt.shape[1] == C, f"weight table has {Wt.shape[1]} bands, cube has {C}"
-    ranges = np.zeros((K, 2), dtype=np.int32)
-    for k in range(K):
-        nz = np.nonzero(Wt[k])[0]
-        ranges[k] = (nz[0], nz[-1] + 1) if len(nz) else (0, 0)
-    wd = torch.as_tensor(Wt.astype(np.float32), device=x.device).contiguous()
+    wd, ranges, K = _device_table(weights, C, x.device)
     T = int(np.prod(lead)) if lead else 1
     out = torch.empty((T, K, H, W), dtype=torch.float32, device=x.device)
-    st = torch.cuda.current_stream(x.device).cuda_stream
-    xf = x.view(T, H * W, C)
-    for t in range(T):                                   # planar (K, H, W) per tile, like the reference's GeoTensor
-        _lib.call("sc_srf_aggregate", xf[t].data_ptr(), H * W, C, wd.data_ptr(), ranges.ctypes.data, K, float(fill_value_default),
-                  out[t].data_ptr(), st)
+    # all stacked scenes in ONE launch; the output is planar (K, H, W) per scene, like the reference's GeoTensor
+    _lib.call("sc_srf_aggregate", x.data_ptr(), T * H * W, H * W, C, wd.data_ptr(), ranges.ctypes.data, K, float(fill_value_default),
+              out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
     return out.view(*lead, K, H, W) if lead else out[0]
+
+
+_TABLES = {}
+
+
+def _device_table(weights, C, device):
+    """(device f32 table, host band ranges, K) of a weight table, cached per table object / device"""
+    key = (id(weights), str(device))
+    ent = _TABLES.get(key)
+    if ent is None or ent[0] is not weights:
+        Wt = np.asarray(weights.detach().cpu() if torch.is_tensor(weights) else weights, dtype=np.float64)
+        K = Wt.shape[0]
+        assert Wt.shape[1] == C, f"weight table has {Wt.shape[1]} bands, cube has {C}"
+        ranges = np.zeros((K, 2), dtype=np.int32)
+        for k in range(K):
+            nz = np.nonzero(Wt[k])[0]
+            ranges[k] = (nz[0], nz[-1] + 1) if len(nz) else (0, 0)
+        wd = torch.as_tensor(Wt.astype(np.float32), device=device).contiguous()
+        if len(_TABLES) > 64:
+            _TABLES.clear()
+        ent = _TABLES[key] = (weights, wd, ranges, K)
+    return ent[1], ent[2], ent[3]

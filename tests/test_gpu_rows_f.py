@@ -273,3 +273,33 @@ def test_emit_scene_prediction_tiled_equals_whole_scene_semantics():
     x, mf, al = emit.emit_model_input(raw, wl, template=synthetic.synthetic_template(S), column_step=4)
     assert x.shape == (4, 64, 32) and torch.isfinite(x).all() and float(x[0].max()) <= 3500.0 and float(x[1:].max()) <= 120.0
     assert emit.rgb_band_indices(wl) == [int(np.argmin(np.abs(wl - w))) for w in (640, 550, 460)]
+
+
+def test_cube_to_unet_chain_fused_pack_equals_the_dataloader_contract():
+    """configs[2]: the fused pack (producer writing the engine's NHWC input) gives the SAME logits / loss as feeding
+    the materialised (B,4,H,W) batch [clip(mf,0,1e4), R, G, B] through normalize_x, and weight_loss = weight_mag1c."""
+    from starcop_b200 import chain, features
+    cube_np, t73, _ = synthetic.aviris_cube(2, size=64, bands=125, seed=3)
+    cube = torch.from_numpy(cube_np).to(DEV)
+    sl = slice(52, 125)
+    rgb = chain.rgb_bands(380.0 + 5.0 * np.arange(125))
+    y = (torch.rand(2, 1, 64, 64, device=DEV) > 0.9).float()
+    for mode in ("f32", "bf16"):
+        torch.manual_seed(4)
+        m = get_model(default_settings(pos_weight=1.0, compute_dtype=mode), None).to(DEV).eval()
+        a = chain.cube_batch(m, cube, t73, sl, rgb, output=y, materialize_input=True)
+        b = chain.cube_batch(m, cube, t73, sl, rgb, output=y)
+        mf, _ = mag1c.mag1c_tiles(cube, t73, sl, num_iter=30)
+        assert torch.equal(a["input"][:, 0], mf.clamp(0, 10000))
+        for k, bi in enumerate(rgb):
+            assert torch.equal(a["input"][:, 1 + k], cube[..., bi])
+        assert torch.equal(a["weight_loss"], features.weight_mag1c(a["input"][:, 0:1]))
+        with torch.no_grad():
+            la = m(a["input"])
+            lb = m.network._forward_impl(b["input"], None, False, record=False)
+        assert torch.equal(la, lb)
+        m.train()
+        torch.manual_seed(4)
+        m2 = get_model(default_settings(pos_weight=1.0, compute_dtype=mode), None).to(DEV).train()
+        l1, l2 = m.train_step_fused(a), m2.train_step_fused(b)
+        assert l1.item() == l2.item() and torch.equal(m.network.flat_params, m2.network.flat_params)

@@ -206,3 +206,113 @@ def test_load_settings_yaml_and_hydra_style_overrides(tmp_path):
         st.load_settings(str(y), ["model.lr"])
     d = st.load_settings(None, ["model.pos_weight=15"])
     assert d.model.pos_weight == 15 and d.dataset.input_products == st.HYPERSTARCOP_PRODUCTS
+
+
+# ---- SURVEY 8(f) host logic (no GPU) -------------------------------------------------------------------------------
+def test_synthetic_datamodule_contract_and_chip_count():
+    """Permian2019DataModule surface over synthetic scenes: 9 scenes x 49 windows = 441 chips (the reference
+    notebook's printout), the STARCOPDataset item dict, weighted sampling over add_sample_weight."""
+    import torch
+    from starcop_b200 import tiling
+    from starcop_b200.datamodule import get_dataset
+    from starcop_b200.settings import default_settings
+    st = default_settings()
+    st.dataloader.num_workers = 0
+    dm = get_dataset(st, n_train_scenes=9, n_test_scenes=2)
+    dm.prepare_data()
+    assert len(dm.train_dataset) == 441 and len(dm.val_dataset) == 2 and len(dm.train_dataset_non_tiled) == 9
+    it = dm.train_dataset[0]
+    assert set(it) == {"input", "output", "weight_loss", "id", "has_plume"}
+    assert it["input"].shape == (4, 128, 128) and it["output"].shape == (1, 128, 128) and it["input"].dtype == torch.float32
+    assert it["id"].endswith("_r0_c0_w128_h128") and isinstance(it["has_plume"], int)
+    rec = dm.train_dataset.records[10]
+    r, c, h, w = rec["window"]
+    assert (r, c, h, w) == (64, 192, 128, 128) and rec["id"].endswith(f"_r{r}_c{c}_w{w}_h{h}")
+    scene = dm.train_dataset.scenes[rec["scene"]]
+    assert rec["has_plume"] == (float(scene["output"][:, r:r + h, c:c + w].sum()) / (h * w) > 10 / 64 ** 2)
+    g = torch.Generator().manual_seed(0)
+    b = next(iter(dm.train_dataloader(batch_size=8, generator=g)))
+    assert b["input"].shape == (8, 4, 128, 128) and b["has_plume"].shape == (8,) and len(b["id"]) == 8
+    # the sampler favours the rarer class like the reference's 1/fraction weights
+    flags = [r["has_plume"] for r in dm.train_dataset.records]
+    w = tiling.add_sample_weight(flags)
+    frac = sum(flags) / len(flags)
+    assert abs(w[flags.index(True)] - 1 / frac) < 1e-12 and abs(w[flags.index(False)] - 1 / (1 - frac)) < 1e-12
+    v = next(iter(dm.val_dataloader(batch_size=1)))
+    assert v["input"].shape == (1, 4, 512, 512)
+
+
+def test_validation_aggregate_matches_reference_pandas_path():
+    import torch
+    from oracle import validation as ov
+    from starcop_b200 import validation
+    rng = np.random.default_rng(0)
+    rows = []
+    for i in range(12):
+        lab = int(rng.choice([0, 0, 300, 5000]))
+        tp = int(rng.integers(0, lab + 1)) if lab else 0
+        fp = int(rng.integers(0, 400))
+        rows.append({"id": f"t{i}", "TP": tp, "FN": lab - tp, "FP": fp, "TN": 128 * 128 - lab - fp, "label_pixels_plume": lab,
+                     "pred_classification": int(tp + fp > 40), "has_plume": int(lab > 0)})
+    rows[0].update(label_pixels_plume=0, TP=0, FN=0, TN=128 * 128 - rows[0]["FP"])      # the groups the reference indexes exist
+    rows[1].update(label_pixels_plume=300, TP=100, FN=200, TN=128 * 128 - 300 - rows[1]["FP"])
+    rows[2].update(label_pixels_plume=5000, TP=4000, FN=1000, TN=128 * 128 - 5000 - rows[2]["FP"])
+    gcm = torch.tensor([[sum(r["TN"] for r in rows), sum(r["FP"] for r in rows)], [sum(r["FN"] for r in rows), sum(r["TP"] for r in rows)]])
+    sweep = [(0.9, gcm.clone()), (0.5, gcm.clone())]
+    out_rows, rep = validation.aggregate(rows, gcm, sweep)
+    _, ref = ov.aggregate(rows, gcm, None)
+    for k, v in ref.items():
+        if torch.is_tensor(v):
+            assert torch.equal(rep[k], v), k
+        else:
+            assert (np.isnan(v) and np.isnan(rep[k])) or rep[k] == pytest.approx(v, rel=1e-12, abs=0), k
+    assert [r["difficulty"] for r in out_rows[:3]] == ["hard", "hard", "easy"]
+    assert [d["threshold"] for d in rep["thresholded"]] == [0.9, 0.5] and "FPR" in rep["thresholded"][0]
+
+
+def test_srf_weight_table_matches_reference_recipe():
+    import pandas as pd
+    from oracle import srf as osrf
+    from starcop_b200 import srf
+    rng = np.random.default_rng(1)
+    centers = 380.0 + 5.01 * np.arange(125)
+    wl = np.arange(400.0, 990.0, 0.5)
+    resp = np.stack([np.exp(-0.5 * ((wl - c) / s) ** 2) for c, s in ((450, 15), (560, 20), (665, 12), (842, 45))])
+    W = srf.srf_weight_table(wl, resp, centers)
+    assert np.allclose(W.sum(1), 1.0, atol=1e-12)
+    cube = rng.uniform(1, 5, size=(125, 5, 6)).astype(np.float32)
+    df = pd.DataFrame(resp.T, index=wl, columns=list("abcd"))
+    ref = osrf.transform_to_srf(cube, list("abcd"), df, centers)
+    assert np.allclose(np.einsum("kc,chw->khw", W, cube.astype(np.float64)), ref, rtol=1e-6)
+    with pytest.raises(ValueError):
+        srf.srf_weight_table(np.array([100.0, 500.0]), np.ones((1, 2)), centers)          # outside the band range: interp1d raises
+
+
+def test_augmentation_matrices_compose_like_the_reference_operators():
+    import torch
+    from oracle import augment as oa
+    from starcop_b200 import augment
+    H, W = 12, 16
+    x = torch.rand(2, H, W, generator=torch.Generator().manual_seed(0))
+    for ang, hf, vf in [(0, 1, 0), (0, 0, 1), (37.0, 0, 0), (-63.0, 1, 1), (90.0, 1, 0)]:
+        p = {"angle": torch.tensor([ang]), "hflip": torch.tensor([bool(hf)]), "vflip": torch.tensor([bool(vf)])}
+        m = augment.dst_to_src_matrices(p, H, W)[0].double()
+        ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float64), torch.arange(W, dtype=torch.float64), indexing="ij")
+        sx, sy = m[0] * xs + m[1] * ys + m[2], m[3] * xs + m[4] * ys + m[5]
+        grid = torch.stack([2 * sx / (W - 1) - 1, 2 * sy / (H - 1) - 1], -1)[None].float()
+        mine = torch.nn.functional.grid_sample(x[None], grid, mode="bilinear", padding_mode="zeros", align_corners=True)[0]
+        assert (mine - oa.augment_sample(x, ang, hf, vf)).abs().max().item() < 5e-6
+    d = augment.draw_params(1000, torch.Generator().manual_seed(1))
+    assert 0.4 < (d["angle"] != 0).float().mean() < 0.6 and d["angle"].abs().max() <= 90 and 0.4 < d["hflip"].float().mean() < 0.6
+
+
+def test_train_entry_point_parses_reference_style_overrides():
+    from starcop_b200 import settings as S
+    ref_cfg = "/root/reference/scripts/configs/config.yaml"
+    st = S.load_settings(ref_cfg if os.path.exists(ref_cfg) else None,
+                         ["model.pos_weight=1", "training.max_epochs=2", "dataloader.batch_size=16", "+model.compute_dtype=bf16",
+                          "dataset.input_products=[mag1c,TOA_AVIRIS_640nm,TOA_AVIRIS_550nm,TOA_AVIRIS_460nm]"])
+    assert st.model.pos_weight == 1 and st.training.max_epochs == 2 and st.model.compute_dtype == "bf16"
+    assert st.dataset.input_products[0] == "mag1c" and st.training.val_check_interval == 0.5
+    import scripts.train as entry
+    assert callable(entry.main)
