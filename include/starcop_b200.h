@@ -16,6 +16,7 @@
  * Implementation selectors (environment, read per call; the tests use them to check two independent kernels of
  * one operator against each other -- they never select a CPU path, there is none):
  *   STARCOP_MAG1C_STREAMING  sc_mag1c_filter: always the streaming kernel (no group-resident fast path)
+ *   STARCOP_MAG1C_NO_TC      sc_mag1c_filter: the fp64-FMA group-resident kernel instead of the tensor-core one
  *   STARCOP_RATIO_NOCLUSTER / STARCOP_RATIO_CLUSTER   sc_ratio_product: force the single-CTA / the cluster select
  *   STARCOP_BN_NOFLAT        sc_bn_bwd_reduce: always the register-streaming kernel (no cp.async.bulk ring)
  *   STARCOP_NO_WGRAD_HALO    sc_tc_conv_wgrad: always the per-tap kernel (no halo-patch kernel for the thin layers)
@@ -182,6 +183,9 @@ int64_t sc_mag1c_smem_bytes(int S, int pmax, int elem_bytes);   /* must be <= 22
 int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_t* pix_idx, const int32_t* counts,
                     int pmax, const double* tmpl, void* mf_out, void* albedo_out, int G, int S,
                     int num_iter, double alpha, int fp64, int skip_le, int* status, void* stream);
+/* diagnostics: clock64 stamps of group 0 at the phase boundaries of the last tensor-core mag1c launch
+ * (start, loaded, centred, MMAs done, covariance assembled, inverse done, rmf end, iteration 0 end, end) */
+int sc_debug_mag1c_clocks(long long* out16);
 
 /* ---- A11/A13: band ratio product (starcop/data/feature_extration.py:32-56) ------------------
  * per tile: exact 5/95 percentiles (np.percentile linear) of each band by radix select, inlier

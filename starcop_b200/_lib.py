@@ -44,6 +44,7 @@ SIGNATURES = {
     "sc_adam_step_dev": [P, P, P, P, L, P, F, F, F, P, F, P],
     "sc_mag1c_smem_bytes": [I, I, I],
     "sc_mag1c_filter": [P, L, P, P, I, P, P, P, I, I, I, D, I, I, P, P],
+    "sc_debug_mag1c_clocks": [P],
     "sc_ratio_workspace_bytes": [I, L],
     "sc_ratio_product": [P, P, P, I, L, F, F, P, P],
     "sc_weight_mag1c": [P, P, L, P],

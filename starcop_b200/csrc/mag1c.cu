@@ -18,6 +18,13 @@
 
 using namespace sc;
 
+namespace sc {
+// mag1c_tc.cu: group-resident kernel with the covariance on the tensor cores
+int mag1c_tc_launch(const float* x, int64_t pixel_stride, const int32_t* pix_idx, const int32_t* counts, int pmax,
+                    const double* tmpl, float* mf_out, float* al_out, int G, int S, int num_iter, int skip_le,
+                    int* status, cudaStream_t st);
+}
+
 namespace {
 
 constexpr int kThreads = 128;
@@ -707,7 +714,12 @@ extern "C" int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_
     return SC_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e;
-  // group-resident fast path: fp32 radiance, no diagonal loading, <= 512 pixels per group (the AVIRIS case)
+  // group-resident fast paths: fp32 radiance, no diagonal loading, <= 512 pixels per group (the AVIRIS case)
+  if (!fp64 && alpha == 0.0 && pmax <= kResMaxP && !getenv("STARCOP_MAG1C_STREAMING") && !getenv("STARCOP_MAG1C_NO_TC")) {
+    const int r = mag1c_tc_launch((const float*)x, pixel_stride, pix_idx, counts, pmax, tmpl, (float*)mf_out,
+                                  (float*)albedo_out, G, S, num_iter, skip_le, status, st);
+    if (r != SC_ERR_UNSUPPORTED) return r;
+  }
   if (!fp64 && alpha == 0.0 && pmax <= kResMaxP && res_smem_bytes(S) <= 227 * 1024 && !getenv("STARCOP_MAG1C_STREAMING")) {
     const size_t rs = res_smem_bytes(S);
     e = cudaFuncSetAttribute(mag1c_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs);
