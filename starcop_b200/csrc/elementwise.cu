@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const T* __restri
   }
 }
 
-// Flat variant for the dense full-resolution layers (C in {16, 32, 64}, dz and y contiguous): both tensors are
+// Flat variant for the large contiguous layers (C <= 256 a multiple of 8 -- 16 / 32 / 64 of the decoder, 96 / 144 of the
+// encoder's expanded tensors; threads beyond PL * CV idle when C / 8 does not divide the block --, dz and y contiguous): both tensors are
 // plain arrays, so a CTA streams them through shared memory with 1-D bulk copies (cp.async.bulk, a ring of
 // three chunks in flight) instead of holding every in-flight byte in registers -- the register-bound kernel
 // above tops out at ~2.8 TB/s on these layers with the 296-CTA cap of the partial-row protocol.
@@ -424,6 +425,7 @@ bn_bwd_reduce_flat_kernel(const T* __restrict__ dz, const T* __restrict__ y, con
   uint64_t* full = reinterpret_cast<uint64_t*>(fsm + (size_t)kFlatStages * 2 * chunk_bytes);
   double* sm = reinterpret_cast<double*>(fsm);          // [PL][CV][16] reduction scratch, aliases the (drained) ring
   const int tid = threadIdx.x, cv = tid % CV, pl = tid / CV;
+  const bool active = pl < PL;                                    // C / 8 need not divide the block size
   const int64_t nchunks = (P + PPC - 1) / PPC;
   const int64_t my_n = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   if (tid == 0) {
@@ -462,7 +464,7 @@ bn_bwd_reduce_flat_kernel(const T* __restrict__ dz, const T* __restrict__ y, con
 #pragma unroll
     for (int u = 0; u < kFlatPixPerThread; ++u) {
       const int pp = pl + u * PL;
-      if (p0 + pp < P) {
+      if (active && p0 + pp < P) {
         const f8 yv = load8<T>(by + (size_t)pp * C + cv * 8);
         const f8 g = load8<T>(bg + (size_t)pp * C + cv * 8);
 #pragma unroll
@@ -486,11 +488,13 @@ bn_bwd_reduce_flat_kernel(const T* __restrict__ dz, const T* __restrict__ y, con
       phase ^= 1;
     }
   }
-  double* mine = sm + ((size_t)pl * CV + cv) * 16;
+  if (active) {
+    double* mine = sm + ((size_t)pl * CV + cv) * 16;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    mine[k] = s[k];
-    mine[8 + k] = q[k];
+    for (int k = 0; k < 8; ++k) {
+      mine[k] = s[k];
+      mine[8 + k] = q[k];
+    }
   }
   __syncthreads();
   double* row = partials + (int64_t)blockIdx.x * 2 * C;
@@ -508,7 +512,7 @@ extern "C" int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void
                                 int C, int dtype, void* stream) {
   if (!dz || !y || !red || !nrows_host || C % 8 || ldy % 8 || lddz % 8) return SC_ERR_BAD_ARG;
   int64_t P = (int64_t)N * H * W;
-  if (!pooled && lddz == C && ldy == C && (C == 16 || C == 32 || C == 64) && P >= (int64_t)1 << 18 &&
+  if (!pooled && lddz == C && ldy == C && C <= 256 && P >= (int64_t)1 << 18 &&
       !(reinterpret_cast<uintptr_t>(dz) & 15) && !(reinterpret_cast<uintptr_t>(y) & 15) && !getenv("STARCOP_BN_NOFLAT")) {
     const int esz = dtype == SC_F32 ? 4 : 2;
     const int PPC = (kFlatThreads / (C / 8)) * kFlatPixPerThread;

@@ -123,9 +123,12 @@ def test_depthwise(dtype, c, stride, hw, fused):
 @pytest.mark.parametrize("c,hw,act,up2,res", [(16, 16, ACT_RELU6, False, False), (96, 8, ACT_NONE, False, True),
                                               (1280, 2, ACT_RELU6, True, False), (32, 16, ACT_RELU, True, False),
                                               (2064, 2, ACT_RELU, False, False),
-                                              # >= 2^18 pixels, contiguous, C in {16, 32, 64}: the bulk-copy ("flat")
+                                              # >= 2^18 pixels, contiguous, C <= 256: the bulk-copy ("flat")
                                               # backward-reduce kernel, with a ragged last chunk
-                                              (16, 304, ACT_RELU, False, False), (64, 300, ACT_RELU6, False, False)])
+                                              (16, 304, ACT_RELU, False, False), (64, 300, ACT_RELU6, False, False),
+                                              # the same kernel when C / 8 does not divide its block (idle threads):
+                                              # the encoder's expanded tensors
+                                              (96, 296, ACT_RELU6, False, False), (144, 300, ACT_RELU6, False, False)])
 def test_batchnorm_train_forward_backward(dtype, c, hw, act, up2, res):
     torch.manual_seed(2)
     N = 3
