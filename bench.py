@@ -535,6 +535,22 @@ def main():
     torch.cuda.synchronize()
     e2e_run(args.steps)
     ms_e2e, _ = timed(step_e2e, args.steps, 0)
+    collective = None
+    if world > 1 and graphed is not None:
+        # exposed time of the data-parallel exchange: the same graphed step captured WITHOUT the gradient all-reduce
+        # (weights then drift apart across ranks, which is why this leg runs last), max over ranks like every timing
+        nosync = model.make_graphed_train_step(resident, grad_sync=None, warmup=1)
+        ms_ns, _ = timed(lambda: nosync(resident), args.steps, 3)
+        nbytes = model.network.flat_grads.numel() * 4
+        split = model.network.decoder_grad_offset()
+        collective = {"exposed_ms_per_step": (ms - ms_ns) / args.steps, "ms_per_step_without_exchange": ms_ns / args.steps,
+                      "bytes_per_step": nbytes,
+                      "buckets": ([{"what": "decoder + head, all-reduce launched when their weight gradients are issued (runs under "
+                                            "the encoder's backward)", "bytes": nbytes - 4 * split},
+                                   {"what": "encoder, after the backward pass", "bytes": 4 * split}]
+                                  if getattr(grad_sync, "bucketed", False) else [{"what": "whole arena after the backward pass", "bytes": nbytes}]),
+                      "backend": "NCCL all-reduce (sum) inside the step's CUDA graph; 1/world folded into Adam"}
+        nosync = None
     sampler.stop_flag = True
 
     tiles = world * B * args.steps
@@ -604,6 +620,7 @@ def main():
             "largest_gemm_probe": probe,
             "cpu_baseline": cpu, "gpu_eager_baseline": eager, "parity": parity, "spectral_products": spectral,
             "configs2_cube_to_unet_chain": chain_res, "configs4_emit_inference_sweep": emit_res,
+            "collective": collective,
         }
         emit(line)
     if world > 1:

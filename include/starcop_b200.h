@@ -18,6 +18,8 @@
  *   STARCOP_MAG1C_STREAMING  sc_mag1c_filter: always the streaming kernel (no group-resident fast path)
  *   STARCOP_MAG1C_NO_TC      sc_mag1c_filter: the fp64-FMA group-resident kernel instead of the tensor-core one
  *   STARCOP_RATIO_NOCLUSTER / STARCOP_RATIO_CLUSTER   sc_ratio_product: force the single-CTA / the cluster select
+ *   STARCOP_RATIO_CLUSTER8 / STARCOP_RATIO_CLUSTER12   sc_ratio_product: the eight-CTA (one band at a time) cluster kernel /
+ *                            twelve-CTA clusters instead of the automatic choice between sixteen and twelve
  *   STARCOP_BN_NOFLAT        sc_bn_bwd_reduce: always the register-streaming kernel (no cp.async.bulk ring)
  *   STARCOP_NO_WGRAD_HALO    sc_tc_conv_wgrad: always the per-tap kernel (no halo-patch kernel for the thin layers)
  */

@@ -6,6 +6,7 @@
 // monotone integer image of the floats (four ranks at once: k, k+1 for each percentile), then the
 // inlier sum.  Kernel 2: the coalesced, vectorised elementwise product.
 #include <cooperative_groups.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -347,6 +348,306 @@ ratio_cluster_kernel(const float* __restrict__ bg, const float* __restrict__ sig
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Sixteen-CTA cluster variant (tiles of <= 512 x 512 pixels): BOTH bands of a tile are resident, a sixteenth of each
+// per CTA (2 x 64 KB of sort keys), so the two bands share every pass and every cluster barrier (6 barriers per tile
+// instead of 12), each band is read from HBM exactly once and nothing is re-read from L2: HBM traffic = the
+// algorithmic 12 B / pixel.  Eight tiles occupy 128 SMs instead of 64.  The data are stored as the monotone integer
+// image of the floats (the key is computed once, at load), the scans use 16-byte shared-memory loads, and the select
+// is the same exact radix select on the significant digits of key - min as above.
+// ------------------------------------------------------------------------------------------------
+constexpr int kC16 = 16;
+constexpr int kC16Threads = 1024;
+constexpr int kC16MaxSlice = 16384;      // keys per band per CTA: 2 x 64 KB
+constexpr int kC16MaxSlice12 = 21848;    // with 12 CTAs per tile: 2 x 85.3 KB
+
+__global__ void __launch_bounds__(kC16Threads, 1)
+ratio_cluster16_kernel(const float* __restrict__ bg, const float* __restrict__ sig, float* __restrict__ out, int64_t HW,
+                       SelectRanks sr, float zero_value, double* __restrict__ ws) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int crank = (int)cluster.block_rank();
+  const int csize = (int)cluster.num_blocks();               // 16, or 12 when that fills the GPU in fewer waves
+  const int tile = blockIdx.x / csize;
+  extern __shared__ __align__(16) uint32_t keys[];           // [2][slice] sort keys of this CTA's part of both bands
+  __shared__ unsigned int hist[2][2][4][256];                // [ping-pong][band][rank][digit], read remotely
+  __shared__ unsigned int tot[2][4][256];
+  __shared__ uint32_t s_mm[2][2];                            // [band]{min, max} key of this CTA, read remotely
+  __shared__ double s_part[2];                               // local inlier sums, read remotely
+  __shared__ uint32_t s_gmin[2];
+  __shared__ int s_nbp;
+  __shared__ uint32_t prefix[2][4];
+  __shared__ long long rank[2][4];
+  __shared__ double red[2][kC16Threads / 32];
+  __shared__ uint32_t wred[4][kC16Threads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slice = (int)((((HW + csize - 1) / csize) + 3) & ~(int64_t)3);
+  const int64_t start = (int64_t)crank * slice;
+  const int n = (int)(HW - start < 0 ? 0 : (HW - start < slice ? HW - start : slice));
+  const int nfull = n / 4;                                   // complete 16-byte groups; <= 3 tail elements
+  uint32_t* kb[2] = {keys, keys + slice};
+
+  // ---- load both bands once, as keys; local min / max ------------------------------------------------------------
+  {
+    uint32_t kmin[2] = {0xffffffffu, 0xffffffffu}, kmax[2] = {0u, 0u};
+#pragma unroll
+    for (int band = 0; band < 2; ++band) {
+      const float* src = (band == 0 ? bg : sig) + (int64_t)tile * HW + start;
+      if ((HW & 3) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        uint4* d4 = reinterpret_cast<uint4*>(kb[band]);
+        for (int i = tid; i < n / 4; i += kC16Threads) {
+          const float4 v = __ldg(s4 + i);
+          const uint4 k = make_uint4(f2key(v.x), f2key(v.y), f2key(v.z), f2key(v.w));
+          d4[i] = k;
+          kmin[band] = min(min(kmin[band], k.x), min(min(k.y, k.z), k.w));
+          kmax[band] = max(max(kmax[band], k.x), max(max(k.y, k.z), k.w));
+        }
+      } else {
+        for (int i = tid; i < n; i += kC16Threads) {
+          const uint32_t k = f2key(src[i]);
+          kb[band][i] = k;
+          kmin[band] = min(kmin[band], k);
+          kmax[band] = max(kmax[band], k);
+        }
+      }
+    }
+#pragma unroll
+    for (int band = 0; band < 2; ++band) {
+      const uint32_t a = __reduce_min_sync(0xffffffffu, kmin[band]), b = __reduce_max_sync(0xffffffffu, kmax[band]);
+      if (lane == 0) {
+        wred[2 * band][warp] = a;
+        wred[2 * band + 1][warp] = b;
+      }
+    }
+    __syncthreads();
+    if (warp < 4) {
+      const uint32_t v = wred[warp][lane];
+      const uint32_t r = (warp & 1) ? __reduce_max_sync(0xffffffffu, v) : __reduce_min_sync(0xffffffffu, v);
+      if (lane == 0) s_mm[warp >> 1][warp & 1] = r;
+    }
+    cluster.sync();
+    if (warp < 2) {                                            // warp = band: cluster-wide min / max
+      uint32_t a = 0xffffffffu, b = 0u;
+      if (lane < csize) {
+        const uint32_t* r = cluster.map_shared_rank(&s_mm[warp][0], lane);
+        a = r[0];
+        b = r[1];
+      }
+      a = __reduce_min_sync(0xffffffffu, a);
+      b = __reduce_max_sync(0xffffffffu, b);
+      if (lane == 0) {
+        s_gmin[warp] = a;
+        const uint32_t range = b - a;
+        wred[0][warp] = range ? 32 - __clz(range) : 1;         // significant bits of this band
+      }
+      if (lane < 4) {
+        prefix[warp][lane] = 0;
+        rank[warp][lane] = sr.r[lane];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const int nb = max((int)wred[0][0], (int)wred[0][1]);
+      s_nbp = 8 * ((nb + 7) / 8);
+    }
+    __syncthreads();
+  }
+  const int nbp = s_nbp, npass = nbp / 8;
+  const uint32_t gmin[2] = {s_gmin[0], s_gmin[1]};
+  int pp = 0;
+  // ---- radix select of the four ranks of both bands over the significant digits ---------------------------------------
+  for (int pass = 0; pass < npass; ++pass, pp ^= 1) {
+    const int shift = nbp - 8 * (pass + 1);
+    for (int i = tid; i < 2 * 4 * 256; i += kC16Threads) (&hist[pp][0][0][0])[i] = 0;
+    uint32_t pf[2][4];
+    int uq[2][4];
+#pragma unroll
+    for (int band = 0; band < 2; ++band)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        pf[band][q] = prefix[band][q];
+        uq[band][q] = q;
+        for (int q2 = q - 1; q2 >= 0; --q2)
+          if (pf[band][q2] == pf[band][q]) uq[band][q] = q2;   // ranks with equal prefixes share a histogram
+      }
+    __syncthreads();
+#pragma unroll
+    for (int band = 0; band < 2; ++band) {
+      const uint4* k4 = reinterpret_cast<const uint4*>(kb[band]);
+      const uint32_t gm = gmin[band];
+      unsigned int* hb = &hist[pp][band][0][0];
+      // one element: a warp whose 32 elements all fall in ONE bucket (constant / nodata regions) adds once
+      auto add = [&](unsigned int* h, uint32_t b, bool hit) {
+        int all_same;
+        __match_all_sync(0xffffffffu, hit ? b : 0xffffffffu, &all_same);
+        if (all_same) {
+          if (hit && lane == 0) atomicAdd(h + b, 32u);
+        } else if (hit) {
+          atomicAdd(h + b, 1u);
+        }
+      };
+      if (pass == 0) {
+        // every element counts, the four ranks share one histogram (all prefixes are empty)
+        for (int i0 = 0; i0 < nfull; i0 += kC16Threads) {      // warp-uniform trip count
+          const int i = i0 + tid;
+          const bool ok = i < nfull;
+          uint4 kv = make_uint4(0, 0, 0, 0);
+          if (ok) kv = k4[i];
+          add(hb, ((kv.x - gm) >> shift) & 255u, ok);
+          add(hb, ((kv.y - gm) >> shift) & 255u, ok);
+          add(hb, ((kv.z - gm) >> shift) & 255u, ok);
+          add(hb, ((kv.w - gm) >> shift) & 255u, ok);
+        }
+        if (warp == 0) {
+          const int i = 4 * nfull + lane;
+          const bool ok = lane < 4 && i < n;
+          add(hb, (((ok ? kb[band][i] : gm) - gm) >> shift) & 255u, ok);
+        }
+      } else {
+        // only the elements whose upper digits equal one of the (<= 4, usually 2) distinct prefixes matter: most
+        // warps skip a group after a subtract, a shift and the compares
+        uint32_t up[4];
+        int sl[4], nu = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (uq[band][q] == q) {
+            up[nu] = pf[band][q] >> (shift + 8);
+            sl[nu] = q;
+            ++nu;
+          }
+        auto visit = [&](uint32_t key, bool ok) {
+          const uint32_t rk = key - gm, u = rk >> (shift + 8);
+          bool any = false;
+          for (int j = 0; j < nu; ++j) any |= ok && u == up[j];
+          if (!__any_sync(0xffffffffu, any)) return;
+          for (int j = 0; j < nu; ++j) add(hb + sl[j] * 256, (rk >> shift) & 255u, ok && u == up[j]);
+        };
+        for (int i0 = 0; i0 < nfull; i0 += kC16Threads) {
+          const int i = i0 + tid;
+          const bool ok = i < nfull;
+          uint4 kv = make_uint4(0, 0, 0, 0);
+          if (ok) kv = k4[i];
+          visit(kv.x, ok);
+          visit(kv.y, ok);
+          visit(kv.z, ok);
+          visit(kv.w, ok);
+        }
+        if (warp == 0) {
+          const int i = 4 * nfull + lane;
+          const bool ok = lane < 4 && i < n;
+          visit(ok ? kb[band][i] : gm, ok);
+        }
+      }
+    }
+    __syncthreads();
+    cluster.sync();
+    for (int o = tid; o < 2 * 4 * 256; o += kC16Threads) {    // every CTA sums the histograms of the whole cluster itself
+      const int band = o >> 10, q = (o >> 8) & 3, b = o & 255;
+      unsigned int t = 0;
+      if (uq[band][q] == q) {
+        for (int r = 0; r < csize; ++r) t += cluster.map_shared_rank(&hist[pp][band][q][b], r)[0];
+      }
+      tot[band][q][b] = t;
+    }
+    __syncthreads();
+    if (warp < 8) {
+      // warp (band, q) finds the bucket holding rank[band][q]: 8 bins per lane, warp scan of the lane totals
+      const int band = warp >> 2, q = warp & 3;
+      const unsigned int* tq = tot[band][uq[band][q]];
+      unsigned int c8[8], ls = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        c8[k] = tq[lane * 8 + k];
+        ls += c8[k];
+      }
+      unsigned int incl = ls;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      const long long r = rank[band][q];
+      const long long excl = (long long)incl - ls;
+      if (r >= excl && r < (long long)incl) {
+        long long rr = r - excl;
+        int k = 0;
+        for (; k < 7; ++k) {
+          if (rr < (long long)c8[k]) break;
+          rr -= c8[k];
+        }
+        rank[band][q] = rr;
+        prefix[band][q] = pf[band][q] | ((uint32_t)(lane * 8 + k) << shift);
+      }
+    }
+    __syncthreads();
+  }
+  // ---- percentile bounds (np.percentile linear interpolation) and the inlier sums -----------------------------------
+  double lo[2], hi[2], sacc[2] = {0.0, 0.0};
+#pragma unroll
+  for (int band = 0; band < 2; ++band) {
+    const double a0 = key2f(prefix[band][0] + gmin[band]), a1 = key2f(prefix[band][1] + gmin[band]);
+    const double b0 = key2f(prefix[band][2] + gmin[band]), b1 = key2f(prefix[band][3] + gmin[band]);
+    lo[band] = np_lerp(a0, a1, sr.t_lo);
+    hi[band] = np_lerp(b0, b1, sr.t_hi);
+    for (int i = tid; i < n; i += kC16Threads) {
+      const double v = (double)key2f(kb[band][i]);
+      if (v >= lo[band] && v <= hi[band]) sacc[band] += v;
+    }
+    sacc[band] = warp_sum(sacc[band]);
+    if (lane == 0) red[band][warp] = sacc[band];
+  }
+  __syncthreads();
+  if (tid < 2) {
+    double t = 0.0;
+    for (int i = 0; i < kC16Threads / 32; ++i) t += red[tid][i];          // fixed order: deterministic
+    s_part[tid] = t;
+  }
+  cluster.sync();
+  double band_sum[2] = {0.0, 0.0};
+  for (int r = 0; r < csize; ++r) {                                         // fixed order: deterministic
+    const double* rp = cluster.map_shared_rank(&s_part[0], r);
+    band_sum[0] += rp[0];
+    band_sum[1] += rp[1];
+  }
+  if (crank == 0 && tid == 0 && ws) {
+    for (int band = 0; band < 2; ++band) {
+      double* o = ws + ((int64_t)tile * 2 + band) * 3;
+      o[0] = band_sum[band];
+      o[1] = lo[band];
+      o[2] = hi[band];
+    }
+  }
+  // ---- apply from the resident keys ---------------------------------------------------------------------------------
+  const float c = (float)band_sum[0] / (float)band_sum[1];     // numpy: float32 scalar
+  float* op = out + (int64_t)tile * HW + start;
+  if ((HW & 3) == 0) {
+    const uint4* b4 = reinterpret_cast<const uint4*>(kb[0]);
+    const uint4* s4 = reinterpret_cast<const uint4*>(kb[1]);
+    float4* o4 = reinterpret_cast<float4*>(op);
+    for (int i = tid; i < n / 4; i += kC16Threads) {
+      const uint4 bk = b4[i], sk = s4[i];
+      const float b[4] = {key2f(bk.x), key2f(bk.y), key2f(bk.z), key2f(bk.w)};
+      const float sv[4] = {key2f(sk.x), key2f(sk.y), key2f(sk.z), key2f(sk.w)};
+      float r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        r[e] = (c * sv[e] - b[e]) / (b[e] + 1e-6f);
+        if (sv[e] < 1e-6f && b[e] < 1e-6f) r[e] = zero_value;
+      }
+      o4[i] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  } else {
+    for (int i = tid; i < n; i += kC16Threads) {
+      const float b = key2f(kb[0][i]), sv = key2f(kb[1][i]);
+      float r = (c * sv - b) / (b + 1e-6f);
+      if (sv < 1e-6f && b < 1e-6f) r = zero_value;
+      op[i] = r;
+    }
+  }
+  cluster.sync();            // no CTA exits while its shared memory may still be read remotely
+}
+
 }  // namespace
 
 extern "C" int64_t sc_ratio_workspace_bytes(int T, int64_t HW) {
@@ -371,7 +672,68 @@ extern "C" int sc_ratio_product(const float* bg, const float* sig, float* out, i
   cudaStream_t st = (cudaStream_t)stream;
   // measured on B200 (scripts/ratio_bench.py): one cluster per tile wins while the tiles do not fill the GPU
   // (T = 8: 99 us vs 259 us); from ~64 tiles on, two independent CTAs per tile keep more SMs busy
-  if (HW <= (int64_t)kClu * kCluMaxSlice && (T < 64 || getenv("STARCOP_RATIO_CLUSTER")) && !getenv("STARCOP_RATIO_NOCLUSTER")) {
+  // sixteen-CTA clusters (both bands resident: every byte crosses HBM once) whenever the tile fits and the device
+  // co-schedules such a cluster; otherwise the eight-CTA / single-CTA kernels below
+  // measured on B200 (scripts/ratio_bench.py, 512 x 512 tiles): clusters win while the tiles do not fill the GPU with
+  // independent CTAs (T = 8: 89 us); from ~100 tiles on, two independent CTAs per tile keep more SMs busy
+  if (HW <= (int64_t)12 * kC16MaxSlice12 && (T <= 96 || getenv("STARCOP_RATIO_CLUSTER")) && !getenv("STARCOP_RATIO_NOCLUSTER") &&
+      !getenv("STARCOP_RATIO_CLUSTER8")) {
+    // cluster size: 16 CTAs (2 x 64 KB of keys each) or 12 (2 x 86 KB) -- whichever needs fewer cluster-waves x work per
+    // CTA for this T (B200 co-schedules 7 sixteen-CTA clusters: 8 tiles would take two waves)
+    static int active[2] = {-1, -1};                          // max co-resident clusters of 16 / 12 CTAs (per process)
+    const int sizes[2] = {kC16, 12};
+    auto config = [&](cudaLaunchConfig_t& c, cudaLaunchAttribute& a, int cl, unsigned grid) {
+      const int slice = (int)((((HW + cl - 1) / cl) + 3) & ~(int64_t)3);
+      c = cudaLaunchConfig_t{};
+      c.gridDim = dim3(grid);
+      c.blockDim = dim3(kC16Threads);
+      c.dynamicSmemBytes = (size_t)2 * slice * sizeof(uint32_t);
+      c.stream = st;
+      a.id = cudaLaunchAttributeClusterDimension;
+      a.val.clusterDim.x = cl;
+      a.val.clusterDim.y = 1;
+      a.val.clusterDim.z = 1;
+      c.attrs = &a;
+      c.numAttrs = 1;
+    };
+    if (active[0] < 0) {
+      active[0] = active[1] = 0;
+      if (cudaFuncSetAttribute(ratio_cluster16_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+          cudaFuncSetAttribute(ratio_cluster16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               2 * kC16MaxSlice12 * (int)sizeof(uint32_t)) == cudaSuccess) {
+        for (int k = 0; k < 2; ++k) {
+          cudaLaunchConfig_t qc;
+          cudaLaunchAttribute qa;
+          config(qc, qa, sizes[k], (unsigned)sizes[k]);
+          qc.dynamicSmemBytes = (size_t)2 * (k == 0 ? kC16MaxSlice : kC16MaxSlice12) * sizeof(uint32_t);
+          int ncl = 0;
+          if (cudaOccupancyMaxActiveClusters(&ncl, ratio_cluster16_kernel, &qc) == cudaSuccess) active[k] = ncl;
+        }
+      }
+      (void)cudaGetLastError();
+      if (getenv("STARCOP_RATIO_DEBUG")) fprintf(stderr, "ratio clusters co-resident: %d x 16 CTAs, %d x 12 CTAs\n", active[0], active[1]);
+    }
+    int best = -1;
+    double best_cost = 0.0;
+    for (int k = 0; k < 2; ++k) {
+      if (active[k] < 1 || HW > (int64_t)sizes[k] * (k == 0 ? kC16MaxSlice : kC16MaxSlice12)) continue;
+      const double cost = (double)((T + active[k] - 1) / active[k]) / sizes[k];
+      if (best < 0 || cost < best_cost) {
+        best = k;
+        best_cost = cost;
+      }
+    }
+    if (getenv("STARCOP_RATIO_CLUSTER12") && active[1] >= 1) best = 1;
+    if (best >= 0) {
+      cudaLaunchConfig_t cfg;
+      cudaLaunchAttribute at;
+      config(cfg, at, sizes[best], (unsigned)(T * sizes[best]));
+      cudaError_t e = cudaLaunchKernelEx(&cfg, ratio_cluster16_kernel, bg, sig, out, HW, sr, zero_value, (double*)workspace);
+      if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
+      return check_launch();
+    }
+  }
+  if (HW <= (int64_t)kClu * kCluMaxSlice && (T < 64 || getenv("STARCOP_RATIO_CLUSTER") || getenv("STARCOP_RATIO_CLUSTER8")) && !getenv("STARCOP_RATIO_NOCLUSTER")) {
     const int slice = (int)((((HW + kClu - 1) / kClu) + 3) & ~(int64_t)3);
     const size_t smem = (size_t)slice * sizeof(float);
     static bool attr_set = false;

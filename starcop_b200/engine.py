@@ -474,6 +474,7 @@ class UNetEngine:
         up_src[0] = self.conv_bn_act(x, f"{E}.18.0.weight", f"{E}.18.1", 1, 1, ACT_RELU6, training,
                                      out=cat[0].slice(0, 1280), up2=True)
         skip_of_block = {0: 13, 1: 6, 2: 3, 3: 1}
+        self._tape_decoder_start = len(self.tape)          # backward runs the tape in reverse: decoder first
         # ---- decoder
         for i in range(5):
             D = f"decoder.blocks.{i}"
@@ -519,8 +520,13 @@ class UNetEngine:
         ws = self.arena.alloc(_lib.load().sc_head_wgrad_workspace_bytes(z.C))
         call("sc_head_wgrad_tiled", z.ptr, z.ld, dlogits_ptr, self.g["segmentation_head.0.weight"].data_ptr(),
              self.g["segmentation_head.0.bias"].data_ptr(), ws, z.N, z.H, z.W, z.C, self.dtype, self._wgrad_stream())
-        for fn in reversed(self.tape):
-            fn()
+        hook = getattr(self, "on_decoder_grads_issued", None)
+        for k in range(len(self.tape) - 1, -1, -1):
+            self.tape[k]()
+            if k == self._tape_decoder_start and hook is not None:
+                # every head / decoder weight gradient has been issued (main + side stream): the data-parallel
+                # exchange of that bucket can start while the encoder's backward runs
+                hook(self._main_obj, self._side if self.side_wgrad else None)
         self._join_side()
         self.tape = []
         self._tape_generation = -1

@@ -111,6 +111,15 @@ class HyperStarcopUnet(UnetParameters):
         self._materialize()
         return self._flat[1]
 
+    def decoder_grad_offset(self):
+        """element offset in the flat arenas of the first decoder parameter: [offset:] = decoder + head (the part of
+        the gradient the backward pass finishes first)"""
+        self._materialize()
+        for n, p in self.named_parameters():
+            if n.startswith("decoder."):
+                return (p.data_ptr() - self._flat[0].data_ptr()) // 4
+        return 0
+
     # ---- forward / backward -------------------------------------------------------------------
     def _forward_impl(self, x, norm, training, record=None):
         """x: (B,C,H,W) tensor, or a producer ``(B, H, W, device, fill)`` whose ``fill(ptr, ld, dtype, stream)`` writes
@@ -557,7 +566,13 @@ class ModelModule(_Base):
         _lib.call("sc_bce_fused", logits.data_ptr(), y.contiguous().float().data_ptr(),
                   w.contiguous().float().data_ptr() if w is not None else 0, self._pw(), B, n // B,
                   1.0 / n, loss_sum.data_ptr(), grad.data_ptr(), 0, 0, 0, 0, 0, 0, 0, 0, 0, _stream(dev))
+        eng = net._engine
+        eng.on_decoder_grads_issued = None
+        if grad_sync is not None and hasattr(grad_sync, "early"):
+            split = net.decoder_grad_offset()
+            eng.on_decoder_grads_issued = lambda main, side: grad_sync.early(net.flat_grads, split, main, side)
         net._backward_impl(grad)
+        eng.on_decoder_grads_issued = None
         scale = 1.0
         if grad_sync is not None:
             scale = grad_sync(net.flat_grads)

@@ -94,8 +94,9 @@ def test_ratio_product_batched_tiles_vs_oracle():
 
 @pytest.mark.parametrize("h,w", [(512, 512), (99, 77), (64, 50), (3, 5)])
 def test_ratio_cluster_kernel_matches_single_cta_select_and_numpy(h, w, monkeypatch):
-    """the cluster-resident kernel (8 CTAs / tile, histograms merged over DSMEM) finds the SAME exact
-    percentiles as the single-CTA radix select, and numpy's: outputs agree to fp32 rounding of the gain"""
+    """the cluster-resident kernels (16 / 12 CTAs per tile with both bands resident, 8 CTAs per tile one band at a
+    time; histograms merged over DSMEM) find the SAME exact percentiles as the single-CTA radix select, and numpy's:
+    outputs agree to fp32 rounding of the gain"""
     rng = np.random.default_rng(h * 1000 + w)
     T = 3
     bg = np.abs(rng.normal(2.0, 0.7, (T, h, w))).astype(np.float32)
@@ -106,10 +107,14 @@ def test_ratio_cluster_kernel_matches_single_cta_select_and_numpy(h, w, monkeypa
     bg[2] = 3.25                                          # constant band: max == min
     tb, ts = torch.from_numpy(bg).to(DEV), torch.from_numpy(sig).to(DEV)
     r_clu = features.ratio_2c_match_c_from_sums_outlier(tb, ts).cpu().numpy()
-    monkeypatch.setenv("STARCOP_RATIO_NOCLUSTER", "1")
-    r_one = features.ratio_2c_match_c_from_sums_outlier(tb, ts).cpu().numpy()
-    monkeypatch.delenv("STARCOP_RATIO_NOCLUSTER")
+    outs = {}
+    for env in ("STARCOP_RATIO_NOCLUSTER", "STARCOP_RATIO_CLUSTER8", "STARCOP_RATIO_CLUSTER12"):
+        monkeypatch.setenv(env, "1")
+        outs[env] = features.ratio_2c_match_c_from_sums_outlier(tb, ts).cpu().numpy()
+        monkeypatch.delenv(env)
+    r_one = outs["STARCOP_RATIO_NOCLUSTER"]
     assert np.allclose(r_clu, r_one, rtol=1e-6, atol=1e-6)
+    assert np.array_equal(outs["STARCOP_RATIO_CLUSTER8"], r_clu) and np.array_equal(outs["STARCOP_RATIO_CLUSTER12"], r_clu)
     for i in range(T):
         ref = ofeat.ratio_2c_match_c_from_sums_outlier(bg[i].copy(), sig[i].copy())
         assert np.allclose(r_clu[i], ref, rtol=3e-6, atol=3e-6), i

@@ -25,6 +25,15 @@ def _worker(rank, world, port, out):
     flat = torch.full((1000,), float(rank + 1))
     scale = parallel.GradSync()(flat)
     assert scale == 0.5 and torch.all(flat == 3.0)
+    # bucketed exchange: the tail bucket (decoder + head) early, the rest at the end -- same sums as one all-reduce
+    flat = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    gs = parallel.GradSync(bucketed=True)
+    gs.early(flat, 340)
+    assert torch.equal(flat[340:], torch.arange(340, 1000, dtype=torch.float32) * 3) and \
+        torch.equal(flat[:340], torch.arange(340, dtype=torch.float32) * (rank + 1))
+    assert gs(flat) == 0.5 and torch.equal(flat, torch.arange(1000, dtype=torch.float32) * 3)
+    flat = torch.full((10,), float(rank + 1))
+    assert gs(flat) == 0.5 and torch.all(flat == 3.0)          # the next step without an early bucket: one all-reduce
     # parameter broadcast from rank 0
     p = torch.full((10,), float(rank))
     parallel.broadcast_parameters(p, [torch.full((3,), float(rank))])
