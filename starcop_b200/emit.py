@@ -28,12 +28,15 @@ def emit_model_input(raw_data, wavelengths, template=None, fwhm=None, fill_value
 
 
 @torch.no_grad()
-def predict_scene(scene, model, tile=None, divisor=32, batch=8):
+def predict_scene(scene, model, tile=None, divisor=32, batch=8, graphed=True):
     """scene: (C, H, W) CUDA model input -> (1, H, W) sigmoid probabilities on the GPU.
     tile=None: ONE reflect-padded pass over the whole scene (``padded_predict``, the notebook's call);
     tile=T: the scene is reflect-padded to a multiple of T (T % 32 == 0) and cut into T x T tiles that run as batch
-    elements of `batch` tiles per forward; the central crop is returned."""
+    elements of `batch` tiles per forward; the central crop is returned.
+    graphed: every forward is a replay of a CUDA graph captured per input shape (``ModelModule.forward_graphed``);
+    the last, partial batch of tiles is padded to `batch` so that all batches share one graph."""
     model.eval()
+    fwd = model.forward_graphed if graphed and hasattr(model, "forward_graphed") else model
     C, H, W = scene.shape
     if tile is None:
         pr, pc = tiling.find_padding(H, divisor), tiling.find_padding(W, divisor)
@@ -42,11 +45,18 @@ def predict_scene(scene, model, tile=None, divisor=32, batch=8):
         pr, pc = tiling.find_padding(H, tile), tiling.find_padding(W, tile)
     padded = torch.nn.functional.pad(scene[None].float(), (pc[0], pc[1], pr[0], pr[1]), mode="reflect")
     if tile is None:
-        prob = torch.sigmoid(model(padded))[0]
+        prob = torch.sigmoid(fwd(padded))[0]
     else:
         _, _, Hp, Wp = padded.shape
         nh, nw = Hp // tile, Wp // tile
         tiles = padded[0].view(C, nh, tile, nw, tile).permute(1, 3, 0, 2, 4).reshape(nh * nw, C, tile, tile).contiguous()
-        outs = [torch.sigmoid(model(tiles[i:i + batch])) for i in range(0, nh * nw, batch)]
+        nt = nh * nw
+        bsz = min(batch, nt)
+        outs = []
+        for i in range(0, nt, bsz):
+            tb = tiles[i:i + bsz]
+            if tb.shape[0] < bsz and fwd is not model:          # pad the last batch: one graph for every batch
+                tb = torch.cat([tb, tb.new_zeros(bsz - tb.shape[0], C, tile, tile)])
+            outs.append(torch.sigmoid(fwd(tb))[:min(bsz, nt - i)])
         prob = torch.cat(outs).view(nh, nw, 1, tile, tile).permute(2, 0, 3, 1, 4).reshape(1, Hp, Wp)
     return prob[:, pr[0]:pr[0] + H, pc[0]:pc[0] + W]

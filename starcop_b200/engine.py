@@ -229,9 +229,20 @@ class UNetEngine:
              y.N, y.H, y.W, C, self.dtype, self.stream)
         return dy
 
+    @staticmethod
+    def _tc_dims(x, k, stride):
+        """(N, H, W) handed to the tcgen05 kernels.  A 1 x 1 / stride-1 convolution is a per-pixel operation, so when
+        the feature map itself does not tile into 8 x 16 patches (the 8 x 8 maps of 256-pixel tiles at 1/32 resolution)
+        the same pixels are presented as N*H*W/128 images of 8 x 16 (NHWC keeps them contiguous): those layers stay on
+        the tensor cores instead of falling back to the fp32-FMA kernel."""
+        if k == 1 and stride == 1 and (x.W % 16 or x.H % 8) and (x.N * x.H * x.W) % 128 == 0:
+            return (x.N * x.H * x.W) // 128, 8, 16
+        return x.N, x.H, x.W
+
     def _tc_ok(self, x, cin, cout, k, stride):
         """tcgen05 path: bf16 storage, stride 1, 8-aligned channels, spatial patch 8 x 16."""
-        ho, wo = (x.H - 1) // stride + 1, (x.W - 1) // stride + 1
+        _, H, W = self._tc_dims(x, k, stride)
+        ho, wo = (H - 1) // stride + 1, (W - 1) // stride + 1
         return (self.dtype == SC_BF16 and self.use_tc and (stride == 1 or (stride == 2 and k == 3)) and k in (1, 3)
                 and cout % 8 == 0 and wo % 16 == 0 and ho % 8 == 0 and x.ld % 8 == 0)
 
@@ -313,7 +324,8 @@ class UNetEngine:
             # when the tile's K loop is long enough to hide it, else the separate pass over y is cheaper
             want_stats = want_stats and cin * k * k >= 256
             part, n = (self._partials(cout), ctypes.c_int(0)) if want_stats else (0, ctypes.c_int(0))
-            call("sc_tc_conv_fprop", x.ptr, x.ld, wb, y.ptr, y.ld, part, ctypes.byref(n), x.N, x.H, x.W, cin, cout,
+            tn, th, tw = self._tc_dims(x, k, stride)
+            call("sc_tc_conv_fprop", x.ptr, x.ld, wb, y.ptr, y.ld, part, ctypes.byref(n), tn, th, tw, cin, cout,
                  k, k, stride, 0, self.stream)
             return y, ((part, n.value) if want_stats else None)
         wp = self.f32buf(w.numel())
@@ -330,9 +342,10 @@ class UNetEngine:
         lib = _lib.load()
         if tc:
             # deterministic split-K: partial tiles in a workspace, summed in split order by a second kernel
-            nb = lib.sc_tc_conv_wgrad_workspace_bytes(x.N, x.H, x.W, cin, cout, k, k, stride)
+            tn, th, tw = self._tc_dims(x, k, stride)
+            nb = lib.sc_tc_conv_wgrad_workspace_bytes(tn, th, tw, cin, cout, k, k, stride)
             part = self.arena.alloc(nb) if nb > 0 else 0
-            call("sc_tc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), part, x.N, x.H, x.W,
+            call("sc_tc_conv_wgrad", x.ptr, x.ld, dy.ptr, dy.ld, self.g[wname].data_ptr(), part, tn, th, tw,
                  cin, cout, k, k, stride, self._wgrad_stream())
         else:
             nb = lib.sc_conv_wgrad_workspace_bytes(x.N, x.H, x.W, cin, cout, k, k, stride, pad)
@@ -351,7 +364,8 @@ class UNetEngine:
             elif tc:
                 cpad = _lib.load().sc_tc_cin_pad(cout)          # dgrad conv: input channels = Cout
                 wb = self._packed(wname, k, 1, cin, cpad)
-                call("sc_tc_conv_fprop", dy.ptr, dy.ld, wb, dst.ptr, dst.ld, 0, 0, dy.N, dy.H, dy.W, cout, cin, k, k,
+                tn, th, tw = self._tc_dims(dy, k, 1)
+                call("sc_tc_conv_fprop", dy.ptr, dy.ld, wb, dst.ptr, dst.ld, 0, 0, tn, th, tw, cout, cin, k, k,
                      1, acc, self.stream)
             else:
                 wp = self.f32buf(w.numel())

@@ -438,6 +438,39 @@ class ModelModule(_Base):
             raise _lib.StarcopB200Error("starcop_b200 runs on CUDA tensors only (no CPU path)")
         return self.network(x, _norm=self.normalizer.kernel_params(x.device))
 
+    @torch.no_grad()
+    def forward_graphed(self, x):
+        """Eval-mode ``forward`` replayed from a CUDA graph captured once per input shape (whole-scene / tiled
+        inference calls the same shape over and over: ~150 kernel launches become one cudaGraphLaunch).  The graph
+        reads the live weights and running statistics (they are re-packed / re-folded inside the graph), so it stays
+        valid across optimiser steps.  The returned logits are the graph's static output: consume or clone them before
+        the next call with the same shape."""
+        assert not self.training, "forward_graphed is an inference path: call .eval() first"
+        if not x.is_cuda:
+            raise _lib.StarcopB200Error("starcop_b200 runs on CUDA tensors only (no CPU path)")
+        graphs = self.__dict__.setdefault("_eval_graphs", {})
+        key = (tuple(x.shape), x.dtype, x.device.index)
+        ent = graphs.get(key)
+        if ent is None:
+            static_in = x.clone()
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream(x.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):                               # sizes the eval arenas outside the capture
+                    self.forward(static_in)
+            torch.cuda.current_stream(x.device).wait_stream(side)
+            torch.cuda.synchronize(x.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = self.forward(static_in)
+            if len(graphs) >= 8:
+                graphs.clear()
+            ent = graphs[key] = (g, static_in, out)
+        g, static_in, out = ent
+        static_in.copy_(x, non_blocking=True)
+        g.replay()
+        return out
+
     def training_step(self, batch, batch_idx):
         """model_module.py:69-88."""
         x, y = batch["input"], batch["output"]

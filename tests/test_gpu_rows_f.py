@@ -264,6 +264,10 @@ def test_emit_scene_prediction_tiled_equals_whole_scene_semantics():
             for j in range(0, padded.shape[-1], T):
                 man[:, i:i + T, j:j + T] = torch.sigmoid(model(padded[:, :, i:i + T, j:j + T]))[0]
     assert torch.allclose(tiled, man[:, pr[0]:pr[0] + 150, pc[0]:pc[0] + 139], atol=2e-6)
+    # the CUDA-graph replay (default) and the launch-by-launch path run the same kernels on the same addresses
+    assert torch.equal(tiled, emit.predict_scene(scene, model, tile=T, batch=4, graphed=False))
+    assert torch.equal(whole, emit.predict_scene(scene, model, graphed=False))
+    assert torch.equal(tiled, emit.predict_scene(scene, model, tile=T, batch=4))          # second replay of the cached graph
     # full EMIT front end on a small cube: mag1c_emit -> RGB pick -> rescale -> (4, H32, W32)
     rng = np.random.default_rng(1)
     wl = np.linspace(400.0, 2500.0, 120)

@@ -198,6 +198,37 @@ def test_bf16_mode_tracks_fp32_within_stated_tolerance():
     assert cos(model.network.segmentation_head[0].weight.grad.cpu(), oracle.network.segmentation_head[0].weight.grad) > 0.999
 
 
+def test_256_pixel_tiles_keep_the_deepest_pointwise_convs_on_tcgen05(monkeypatch):
+    """BASELINE.json configs[4] sweeps 256-pixel tiles: their 1/32-resolution maps are 8 x 8, which do not tile into the
+    tensor-core kernel's 8 x 16 patches.  1 x 1 convolutions are per-pixel operations, so the engine presents the same
+    pixels as N*64/128 images of 8 x 16 (engine._tc_dims): no fp32-FMA fallback launches, and the step equals the
+    128-pixel-wide case of the same pixels (pointwise kernels do not care which image a pixel belongs to)."""
+    from starcop_b200 import engine, profiler
+    model = get_model(default_settings(pos_weight=1.0, compute_dtype="bf16"), None).to(DEV).train()
+    batch = to_dev(synthetic.hyperstarcop_batch(4, size=256, seed=7))
+    names = []
+    inner = engine.call
+    monkeypatch.setattr(engine, "call", lambda name, *a: (names.append(name), inner(name, *a))[1])
+    l1 = model.train_step_fused(batch)
+    torch.cuda.synchronize()
+    assert "sc_conv_fprop" not in names and "sc_conv_wgrad" not in names, sorted(set(names))
+    assert names.count("sc_tc_conv_fprop") > 60
+    # reference for the regrouping: the engine's own fp32-FMA kernels on the 8 x 8 maps (no regrouping there)
+    monkeypatch.setattr(engine.UNetEngine, "_tc_dims", staticmethod(lambda x, k, stride: (x.N, x.H, x.W)))
+    torch.manual_seed(1234)
+    ref = get_model(default_settings(pos_weight=1.0, compute_dtype="bf16"), None).to(DEV).train()
+    torch.manual_seed(1234)
+    mod = get_model(default_settings(pos_weight=1.0, compute_dtype="bf16"), None).to(DEV).train()
+    names.clear()
+    lr_ = ref.train_step_fused(batch)
+    assert "sc_conv_fprop" in names                      # 8 x 8 maps fall back without the regrouping
+    monkeypatch.undo()
+    lm_ = mod.train_step_fused(batch)
+    assert abs(lm_.item() - lr_.item()) <= 2e-3 * abs(lr_.item())
+    d = (mod.network.flat_params - ref.network.flat_params).abs().max().item()
+    assert d <= 2.5e-3, d                                # one Adam step of lr 1e-3: every weight moved by <= ~1e-3
+
+
 def test_requires_cuda_and_divisible_by_32():
     _, model = build_pair(1.0)
     with pytest.raises(RuntimeError):
