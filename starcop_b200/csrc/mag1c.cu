@@ -28,7 +28,7 @@ int mag1c_tc_launch(const float* x, int64_t pixel_stride, const int32_t* pix_idx
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kTile = 32;           // pixels staged per shared-memory tile (double buffered)
+constexpr int kTile = 64;           // pixels staged per shared-memory tile (double buffered)
 constexpr double kScaling = 1e5;    // mag1c.py:56
 constexpr double kEpsilon = 1e-9;   // mag1c.py:57
 
@@ -135,8 +135,9 @@ mag1c_kernel(const TS* __restrict__ x, int64_t pixel_stride, const int32_t* __re
   TS* tile0 = reinterpret_cast<TS*>(a_s + kTile);                 // 2 x [kTile][S] staged spectra (double buffer)
   uchar2* rc = reinterpret_cast<uchar2*>(tile0 + 2 * kTile * S);  // packed index -> (row, col)
   int32_t* pidx = reinterpret_cast<int32_t*>(rc + ((NT + 3) & ~3)); // [P] this group's pixel indices (8 B aligned)
-  TS* R_s = reinterpret_cast<TS*>(pidx + ((P + 1) & ~1));           // [P] albedo factor, storage precision
-  TS* mf_s = R_s + P;                                               // [P] current matched-filter value
+  // the per-pixel state of the iteration (albedo factor R and the current matched-filter value, both in the storage
+  // precision) lives in the OUTPUT arrays themselves (one L2-resident read + write per pixel and iteration): 2 x P
+  // elements less shared memory per CTA, which is what lets two EMIT groups (2560 pixels, fp64) share an SM
   __shared__ int ok;
   const int tid = threadIdx.x;
 
@@ -283,19 +284,15 @@ mag1c_kernel(const TS* __restrict__ x, int64_t pixel_stride, const int32_t* __re
           R = xmu / mumu;                                // mag1c.py:330
           mf = (dot - mucit) / (R * nrm);                // mag1c.py:332
         } else {
-          R = (double)R_s[p0 + pp];
-          double mf_old = (double)mf_s[p0 + pp];
+          R = (double)al_out[pix];
+          double mf_old = (double)mf_out[pix];
           double reg = 1.0 / (R * (mf_old + kEpsilon));  // mag1c.py:255
           mf = ((dot - mucit) - reg) / (R * nrm);        // mag1c.py:267
         }
         mf = mf > 0.0 ? mf : 0.0;                        // relu
         TS mfs = (TS)mf;                                 // working values kept in the storage precision
-        if (it == 0) {
-          R_s[p0 + pp] = (TS)R;
-          al_out[pix] = (TS)R;
-        }
-        mf_s[p0 + pp] = mfs;
-        if (last) mf_out[pix] = (TS)((double)mfs * kScaling);
+        if (it == 0) al_out[pix] = (TS)R;
+        mf_out[pix] = last ? (TS)((double)mfs * kScaling) : mfs;
         double a = (double)(TS)R * (double)mfs;
         a_s[pp] = a;
         la += a;
@@ -703,7 +700,7 @@ mag1c_resident_kernel(const float* __restrict__ x, int64_t pixel_stride, const i
 
 extern "C" int64_t sc_mag1c_smem_bytes(int S, int pmax, int elem_bytes) {
   int64_t NT = (int64_t)S * (S + 1) / 2;
-  return (NT + (int64_t)(S + 1) * mag1c_ld(S) + 8 * S + 8 + kTile) * 8 + 2 * (int64_t)kTile * S * elem_bytes + 2 * NT + 32 + (4 + 2 * (int64_t)elem_bytes) * (pmax + 2);
+  return (NT + (int64_t)(S + 1) * mag1c_ld(S) + 8 * S + 8 + kTile) * 8 + 2 * (int64_t)kTile * S * elem_bytes + 2 * NT + 32 + 4 * (int64_t)(pmax + 2);
 }
 
 extern "C" int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_t* pix_idx, const int32_t* counts,

@@ -236,20 +236,21 @@ def mag1c_emit(raw_data, wavelengths, template=None, fwhm=None, fill_value_defau
     invalid = torch.any(x == fill_value_default, dim=-1)                                       # (rows, cols)
     x64 = x.to(torch.float64).contiguous()                                                     # :75
     column_step = column_step or cols
-    starts = list(range(0, cols, column_step))
-    G, pmax = len(starts), rows * column_step
-    # per group: the valid pixels of raw[:, c0:c1] in row-major order of the slice (``raw_data_slice[valid_slice]``)
-    valid = ~invalid
-    flat = torch.arange(rows * cols, device=dev, dtype=torch.int32).view(rows, cols)
-    pix = torch.zeros(G, pmax, dtype=torch.int32, device=dev)
-    cnt = torch.zeros(G, dtype=torch.int32, device=dev)
-    for g, c0 in enumerate(starts):                       # host loop over groups like the reference's; device-side gathers
-        c1 = min(c0 + column_step, cols)
-        v = valid[:, c0:c1]
-        ids = flat[:, c0:c1][v]
-        n = int(ids.numel())
-        pix[g, :n] = ids
-        cnt[g] = n
+    G, pmax = (cols + column_step - 1) // column_step, rows * column_step
+    # per group: the valid pixels of raw[:, c0:c1] in row-major order of the slice (``raw_data_slice[valid_slice]``,
+    # mag1c_emit.py:56-84).  Built for ALL groups at once on the device (the reference loops over the groups on the
+    # host; a per-group loop here would cost one device synchronisation per group -- 621 for a granule): the columns
+    # are padded to G * column_step with invalid pixels, viewed as (G, rows * column_step), and each row is
+    # compacted by a stable sort of the validity flags.
+    cpad = G * column_step
+    valid = torch.zeros(rows, cpad, dtype=torch.bool, device=dev)
+    valid[:, :cols] = ~invalid
+    flat = torch.arange(rows, device=dev, dtype=torch.int32)[:, None] * cols + torch.arange(cpad, device=dev, dtype=torch.int32)[None, :]
+    vg = valid.view(rows, G, column_step).permute(1, 0, 2).reshape(G, pmax)
+    fg = flat.view(rows, G, column_step).permute(1, 0, 2).reshape(G, pmax)
+    order = torch.argsort((~vg).to(torch.uint8), dim=1, stable=True)            # valid pixels first, order kept
+    pix = torch.gather(fg, 1, order).contiguous()
+    cnt = vg.sum(dim=1).to(torch.int32)
     mf = torch.full((rows, cols), float(fill_value_default), dtype=torch.float64, device=dev)
     al = torch.full((rows, cols), float(fill_value_default), dtype=torch.float64, device=dev)
     status = _filter(x64, S, pix, cnt, template, mf, al, S, num_iter, covariance_lerp_alpha, skip_le=0)
