@@ -162,9 +162,14 @@ __global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __rest
 
 extern "C" int64_t sc_bn_partials_bytes(int C) { return (int64_t)(SC_BN_MAX_PARTIALS + 2) * 2 * C * sizeof(double); }
 
+int bn_stats_flat(const void* y, double* partials, int* nrows_host, int64_t P, int C, int dtype, cudaStream_t st);   // below
+
 extern "C" int sc_bn_stats(const void* y, int ldy, double* partials, int* nrows_host, int64_t P, int C, int dtype,
                            void* stream) {
   if (!y || !partials || !nrows_host || C % 8 || ldy % 8 || P <= 0) return SC_ERR_BAD_ARG;
+  if (ldy == C && C <= 256 && P >= (int64_t)1 << 18 && (dtype == SC_F32 || dtype == SC_BF16) &&
+      !(reinterpret_cast<uintptr_t>(y) & 15) && !getenv("STARCOP_BN_NOFLAT"))
+    return bn_stats_flat(y, partials, nrows_host, P, C, dtype, (cudaStream_t)stream);
   RedGeom g = red_geom(C);
   dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
   *nrows_host = (int)grid.x;
@@ -504,6 +509,113 @@ bn_bwd_reduce_flat_kernel(const T* __restrict__ dz, const T* __restrict__ y, con
     for (int j = 0; j < PL; ++j) t += sm[((size_t)j * CV + cvo) * 16 + k];
     row[(k < 8 ? 0 : C) + cvo * 8 + (k & 7)] = t;
   }
+}
+
+// Forward statistics through the same bulk-copy ring (one input stream): sum and sum of squares per channel of a
+// contiguous tensor.  The register kernel (bn_stats_kernel) is capped at 296 CTAs by the partial-row protocol and tops
+// out at ~2.2 TB/s on the megapixel layers.
+template <typename T>
+__global__ void __launch_bounds__(kFlatThreads, 2)
+bn_stats_flat_kernel(const T* __restrict__ y, double* __restrict__ partials, int64_t P, int C) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  const int CV = C / 8, PL = kFlatThreads / CV;
+  const int PPC = PL * 2 * kFlatPixPerThread;                     // pixels per chunk (one tensor: twice the pixels)
+  const uint32_t chunk_bytes = (uint32_t)PPC * C * sizeof(T);
+  T* bufs = reinterpret_cast<T*>(fsm);                            // [stage][PPC*C]
+  uint64_t* full = reinterpret_cast<uint64_t*>(fsm + (size_t)kFlatStages * chunk_bytes);
+  double* sm = reinterpret_cast<double*>(fsm);                    // [PL][CV][16] reduction scratch (drained ring)
+  const int tid = threadIdx.x, cv = tid % CV, pl = tid / CV;
+  const bool active = pl < PL;
+  const int64_t nchunks = (P + PPC - 1) / PPC;
+  const int64_t my_n = blockIdx.x < nchunks ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (tid == 0) {
+    for (int i = 0; i < kFlatStages; ++i) tc::mbar_init(&full[i], 1);
+    tc::fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t i) {
+    const int64_t p0 = (blockIdx.x + i * gridDim.x) * PPC;
+    const int64_t np = P - p0 < PPC ? P - p0 : PPC;
+    const uint32_t bytes = (uint32_t)(np * C * sizeof(T));
+    const int slot = (int)(i % kFlatStages);
+    tc::mbar_arrive_expect_tx(&full[slot], bytes);
+    tc::bulk_load_1d(bufs + (size_t)slot * PPC * C, y + p0 * C, bytes, &full[slot]);
+  };
+  if (tid == 0)
+    for (int i = 0; i < kFlatStages && i < my_n; ++i) issue(i);
+  double s[8], q[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.0;
+  int slot = 0;
+  uint32_t phase = 0;
+  for (int64_t i = 0; i < my_n; ++i) {
+    const int64_t p0 = (blockIdx.x + i * gridDim.x) * PPC;
+    const T* by = bufs + (size_t)slot * PPC * C;
+    tc::mbar_wait(&full[slot], phase);
+    float fs[8], fq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fs[k] = fq[k] = 0.f;
+#pragma unroll
+    for (int u = 0; u < 2 * kFlatPixPerThread; ++u) {
+      const int pp = pl + u * PL;
+      if (active && p0 + pp < P) {
+        const f8 yv = load8<T>(by + (size_t)pp * C + cv * 8);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          fs[k] += yv.v[k];
+          fq[k] = fmaf(yv.v[k], yv.v[k], fq[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      s[k] += (double)fs[k];
+      q[k] += (double)fq[k];
+    }
+    __syncthreads();                                  // every reader of the slot is done
+    if (tid == 0 && i + kFlatStages < my_n) issue(i + kFlatStages);
+    if (++slot == kFlatStages) {
+      slot = 0;
+      phase ^= 1;
+    }
+  }
+  if (active) {
+    double* mine = sm + ((size_t)pl * CV + cv) * 16;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      mine[k] = s[k];
+      mine[8 + k] = q[k];
+    }
+  }
+  __syncthreads();
+  double* row = partials + (int64_t)blockIdx.x * 2 * C;
+  for (int o = tid; o < CV * 16; o += kFlatThreads) {
+    const int cvo = o / 16, k = o % 16;
+    double t = 0.0;
+    for (int j = 0; j < PL; ++j) t += sm[((size_t)j * CV + cvo) * 16 + k];
+    row[(k < 8 ? 0 : C) + cvo * 8 + (k & 7)] = t;
+  }
+}
+
+// shared by sc_bn_stats (declared above its definition)
+template <typename T>
+static int launch_bn_stats_flat(const void* y, double* partials, int* nrows_host, int64_t P, int C, cudaStream_t st) {
+  const int PPC = (kFlatThreads / (C / 8)) * 2 * kFlatPixPerThread;
+  const size_t smem = (size_t)kFlatStages * PPC * C * sizeof(T) + 64;     // >= 32 KB: also the reduction scratch
+  const int64_t nchunks = (P + PPC - 1) / PPC;
+  const int gx = (int)(nchunks < SC_BN_MAX_PARTIALS ? nchunks : SC_BN_MAX_PARTIALS);
+  *nrows_host = gx;
+  cudaError_t e = cudaFuncSetAttribute(bn_stats_flat_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) {
+    g_last_error = e;
+    return SC_ERR_CUDA;
+  }
+  bn_stats_flat_kernel<T><<<gx, kFlatThreads, smem, st>>>((const T*)y, partials, P, C);
+  return check_launch();
+}
+int bn_stats_flat(const void* y, double* partials, int* nrows_host, int64_t P, int C, int dtype, cudaStream_t st) {
+  if (dtype == SC_F32) return launch_bn_stats_flat<float>(y, partials, nrows_host, P, C, st);
+  return launch_bn_stats_flat<__nv_bfloat16>(y, partials, nrows_host, P, C, st);
 }
 
 extern "C" int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void* y, int ldy,
