@@ -182,6 +182,7 @@ extern "C" int sc_bn_stats(const void* y, int ldy, double* partials, int* nrows_
 // block = 32 channels x kRedY row slices: the nrows partial rows are summed kRedY-way in parallel
 // (<= 10 independent loads per thread: these tiny kernels are pure latency)
 constexpr int kRedY = 32;
+constexpr int kRedRows = (SC_BN_MAX_PARTIALS + kRedY - 1) / kRedY;     // partial rows per thread (10)
 __global__ void bn_finalize_kernel(const double* __restrict__ partials, int nrows, int64_t P, int C,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* running_mean, float* running_var, float momentum, float eps,
@@ -192,10 +193,19 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partials, int nrow
   const int c = blockIdx.x * 32 + tx;
   double s1 = 0.0, s2 = 0.0;
   if (training && c < C) {
-#pragma unroll 4
-    for (int r = ty; r < nrows; r += kRedY) {
-      s1 += partials[(int64_t)r * 2 * C + c];
-      s2 += partials[(int64_t)r * 2 * C + C + c];
+    // all of this thread's rows are loaded before the first add: the kernel is one memory latency long, not
+    // nrows / 32 of them (it sits between every convolution and its activation, 62 times per step)
+    double a[kRedRows], b[kRedRows];
+#pragma unroll
+    for (int u = 0; u < kRedRows; ++u) {
+      const int r = ty + u * kRedY;
+      a[u] = r < nrows ? partials[(int64_t)r * 2 * C + c] : 0.0;
+      b[u] = r < nrows ? partials[(int64_t)r * 2 * C + C + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kRedRows; ++u) {      // same order as a sequential loop over the rows
+      s1 += a[u];
+      s2 += b[u];
     }
   }
   sh[0][ty][tx] = s1;
@@ -236,7 +246,8 @@ extern "C" int sc_bn_finalize(const double* sums, int nrows, int64_t P, int C, c
                               float* running_mean, float* running_var, float momentum, float eps,
                               int training, float* scale, float* shift, float* save_mean,
                               float* save_invstd, void* stream) {
-  if (C <= 0 || !scale || !shift || (training && !sums) || (!training && (!running_mean || !running_var)))
+  if (C <= 0 || !scale || !shift || (training && (!sums || nrows > SC_BN_MAX_PARTIALS)) ||
+      (!training && (!running_mean || !running_var)))
     return SC_ERR_BAD_ARG;
   bn_finalize_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, (cudaStream_t)stream>>>(
       sums, nrows, P, C, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift,
@@ -696,10 +707,17 @@ __global__ void bn_bwd_totals_kernel(double* __restrict__ partials, int nrows, i
   const int c = blockIdx.x * 32 + tx;
   double s1 = 0.0, s2 = 0.0;
   if (c < C) {
-#pragma unroll 4
-    for (int r = ty; r < nrows; r += kRedY) {
-      s1 += partials[(int64_t)r * 2 * C + c];
-      s2 += partials[(int64_t)r * 2 * C + C + c];
+    double a[kRedRows], b[kRedRows];
+#pragma unroll
+    for (int u = 0; u < kRedRows; ++u) {
+      const int r = ty + u * kRedY;
+      a[u] = r < nrows ? partials[(int64_t)r * 2 * C + c] : 0.0;
+      b[u] = r < nrows ? partials[(int64_t)r * 2 * C + C + c] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < kRedRows; ++u) {
+      s1 += a[u];
+      s2 += b[u];
     }
   }
   sh[0][ty][tx] = s1;
