@@ -7,7 +7,8 @@ import os
 from ctypes import c_double, c_float, c_int, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libstarcop_b200.so")
+# STARCOP_LIB: load another build of the same library (A/B experiments of compile-time variants)
+LIB_PATH = os.environ.get("STARCOP_LIB") or os.path.join(HERE, "lib", "libstarcop_b200.so")
 
 SC_F32, SC_BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_RELU6 = 0, 1, 2

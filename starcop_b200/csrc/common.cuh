@@ -21,6 +21,37 @@ inline int check_launch() {
 
 constexpr int kNumSMs = 148;  // B200
 
+// ---- programmatic dependent launch (PDL)
+// Every kernel of the train / eval step is launched with cudaLaunchAttributeProgrammaticStreamSerialization and opens with
+// pdl_wait(): griddepcontrol.wait blocks until the preceding kernel of the stream has COMPLETED and flushed its writes, so
+// the data dependencies are exactly those of a plain stream launch, while the launch itself (grid setup, CTA scheduling,
+// parameter / descriptor fetch) overlaps the predecessor's tail; launch_dependents right after it lets the successor do the
+// same once all of this kernel's CTAs are running.  The step is ~580 launches, most of them 5-15 us long, so the
+// per-boundary bubble matters.  STARCOP_PDL=0 falls back to plain launches (A/B measurement).
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifdef SC_PDL_EARLY_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+bool pdl_enabled();   // elementwise.cu: reads STARCOP_PDL once
+
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);     // errors surface through check_launch()
+}
+
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- 8-wide channel vectors: the unit every NHWC bandwidth kernel moves (16 B bf16 / 32 B f32)

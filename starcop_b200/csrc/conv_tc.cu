@@ -104,6 +104,7 @@ extern "C" int sc_tc_pack_weights(const float* w_oihw, void* w_bf16, int Cout, i
 // All of a step's weight re-packs in ONE launch: `descs` is a device table of n jobs (see sc_tc_pack_desc in the
 // header), job j covering output elements [offset_j, offset_{j+1}) of the concatenated index space.
 __global__ void tc_pack_weights_batch_kernel(const sc_tc_pack_desc* __restrict__ descs, int n, int64_t total) {
+  sc::pdl_wait();
   __shared__ int64_t s_off[129];
   for (int i = threadIdx.x; i < n; i += blockDim.x) s_off[i] = descs[i].offset;
   if (threadIdx.x == 0) s_off[n] = total;
@@ -135,7 +136,7 @@ extern "C" int sc_tc_pack_weights_batch(const sc_tc_pack_desc* descs_dev, int n,
   if (!descs_dev || n < 1 || n > 128 || total < 1) return SC_ERR_BAD_ARG;
   int64_t blocks = (total + 255) / 256;
   if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
-  tc_pack_weights_batch_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(descs_dev, n, total);
+  sc::launch_pdl((tc_pack_weights_batch_kernel), (int)blocks, 256, 0, (cudaStream_t)stream, descs_dev, n, total);
   return check_launch();
 }
 
@@ -164,6 +165,7 @@ constexpr int kMaxDynSmem = 227 * 1024;
 template <int KC>
 __global__ void __launch_bounds__(kTcThreads, 2)
 tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, FpropParams p) {
+  sc::pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int ROW_BYTES = KC * 2;
@@ -496,7 +498,7 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
     cudaError_t e = cudaFuncSetAttribute(tc_conv_fprop_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          kMaxDynSmem);                                                       \
     if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                          \
-    tc_conv_fprop_kernel<KC><<<grid, kTcThreads, smem, st>>>(tmA, tmB, p);                                   \
+    sc::launch_pdl((tc_conv_fprop_kernel<KC>), grid, kTcThreads, smem, st, tmA, tmB, p);                                   \
   } while (0)
   if (kc == 64) LAUNCH_FPROP(64);
   else if (kc == 32) LAUNCH_FPROP(32);
@@ -520,46 +522,77 @@ struct WgradParams {
   float* partials;                 // [m_blocks * n_blocks][ksplit][128][block_n] fp32 (ksplit > 1)
 };
 
-// dW += sum over the pixel splits of their partial tiles, in split order (deterministic).  One thread per float4 of
-// a tile: coalesced reads of the (mostly L2-resident) partials, scattered adds into the OIHW gradient.
+// dW += sum over the pixel splits of their partial tiles, in a fixed order (deterministic).  The partial tiles hold the
+// gradient as [tap, ci][co] (co fastest), the OIHW gradient wants [co][ci][tap].  One CTA owns the block
+// (all taps) x (8 input channels) x (8 output channels): it gathers the block with 32-byte row reads (one full sector
+// each), transposes it through shared memory and writes each output channel's 8 * KH * KW contiguous floats.  The
+// splits (up to ~300 for the thin high-resolution layers) are summed in `slices` interleaved slices by different
+// threads -- split k belongs to slice k % slices -- and the slice sums are added in slice order, so the result does not
+// depend on scheduling.  Small blocks keep the grid large: 64 -> 64 3x3 is 64 CTAs, 1376 -> 256 3x3 is 5632.
+// (One scattered 4-byte read-modify-write per element cost 73 us on the 1376 -> 256 layer; one thread per element
+// walking all splits serially cost 46 us on a 16 x 96 weight.)
+constexpr int kWredT = 8;                        // block edge: 8 input x 8 output channels
+constexpr int kWredSliceFloats = 4096;           // scratch for the slice sums (16 KB)
 template <int KC>
 __global__ void __launch_bounds__(256)
 tc_wgrad_reduce_kernel(WgradParams p) {
+  sc::pdl_wait();
   constexpr int SUBS = 128 / KC;
-  const int tile_elems = 128 * p.block_n;
-  const int bn4 = p.block_n / 4;
+  constexpr int CGS = KC / kWredT;               // input-channel groups per chunk
+  __shared__ float slice_s[kWredSliceFloats];
+  __shared__ float tr_s[kWredT][kWredT * 9 + 1];
   const int KK = p.KH * p.KW;
-  const int64_t total4 = (int64_t)p.m_blocks * p.n_blocks * (tile_elems / 4);
-  for (int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; g < total4; g += (int64_t)gridDim.x * blockDim.x) {
-    const int tile_id = (int)(g / (tile_elems / 4));
-    const int e = (int)(g - (int64_t)tile_id * (tile_elems / 4));
-    const int nb = tile_id / p.m_blocks, mb = tile_id - nb * p.m_blocks;
-    const int r = e / bn4, c = (e - r * bn4) * 4;
-    const int sidx = r / KC, cil = r % KC;
-    const int j = mb * SUBS + sidx;
-    if (j >= p.subs_total) continue;
-    const int tap = j / p.cchunks;
-    const int ci = (j - tap * p.cchunks) * KC + cil;
-    if (ci >= p.Cin) continue;
-    const float* base = p.partials + (size_t)tile_id * p.ksplit * tile_elems + (size_t)e * 4;
-    float4 a = __ldcg(reinterpret_cast<const float4*>(base));
-    for (int k = 1; k < p.ksplit; ++k) {
-      const float4 b = __ldcg(reinterpret_cast<const float4*>(base + (size_t)k * tile_elems));
-      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  const int E = KK * kWredT * kWredT;            // elements of one block: 64 (1x1) or 576 (3x3)
+  int slices = kWredSliceFloats / E;
+  slices = slices > 16 ? 16 : slices;
+  if (slices > p.ksplit) slices = p.ksplit;
+  const int co_tiles = (p.Cout + kWredT - 1) / kWredT;
+  const int items = p.cchunks * CGS * co_tiles;
+  const size_t split_stride = (size_t)128 * p.block_n;
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int ct = item % co_tiles;
+    const int cgi = item / co_tiles;
+    const int chunk = cgi / CGS, cg = cgi - chunk * CGS;
+    const int ci0 = chunk * KC + cg * kWredT;
+    if (ci0 >= p.Cin) continue;                  // zero-padded channels of a ragged last chunk (block-uniform)
+    const int co0 = ct * kWredT;
+    const int nb = co0 / p.block_n;              // block_n is a multiple of 16: a block never straddles N blocks
+    const int c0 = co0 - nb * p.block_n;
+    for (int idx = threadIdx.x; idx < E * slices; idx += 256) {
+      const int sl = idx / E, e = idx - sl * E;
+      const int col = e % kWredT;
+      const int t = e / kWredT;
+      const int cil = cg * kWredT + t % kWredT, tap = t / kWredT;
+      const int j = tap * p.cchunks + chunk;
+      const int mb = j / SUBS, sidx = j - mb * SUBS;
+      const float* base = p.partials + (((size_t)(nb * p.m_blocks + mb) * p.ksplit) * 128 + sidx * KC + cil) * p.block_n + c0 + col;
+      float a = 0.f;
+      for (int k = sl; k < p.ksplit; k += slices) a += __ldcg(base + (size_t)k * split_stride);
+      slice_s[idx] = a;
     }
-    const float av[4] = {a.x, a.y, a.z, a.w};
-    const int n0 = nb * p.block_n;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int co = n0 + c + i;
-      if (co < p.Cout) p.dw[((int64_t)co * p.Cin + ci) * KK + tap] += av[i];
+    __syncthreads();
+    for (int e = threadIdx.x; e < E; e += 256) {
+      float a = slice_s[e];
+      for (int sl = 1; sl < slices; ++sl) a += slice_s[sl * E + e];
+      const int col = e % kWredT;
+      const int t = e / kWredT;
+      tr_s[col][(t % kWredT) * KK + t / kWredT] = a;
     }
+    __syncthreads();
+    const int n = min(kWredT, p.Cin - ci0) * KK; // valid contiguous floats per output channel
+    for (int e = threadIdx.x; e < kWredT * n; e += 256) {
+      const int col = e / n, o = e - col * n;
+      const int co = co0 + col;
+      if (co < p.Cout) p.dw[((int64_t)co * p.Cin + ci0) * KK + o] += tr_s[col][o];
+    }
+    __syncthreads();
   }
 }
 
 template <int KC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, WgradParams p) {
+  sc::pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int PIX = 64;                        // pixels (K) per stage: 4 rows x 16 cols
@@ -805,12 +838,10 @@ extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy
     cudaError_t e = cudaFuncSetAttribute(tc_conv_wgrad_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                          kMaxDynSmem);                                                       \
     if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                          \
-    tc_conv_wgrad_kernel<KC><<<grid, kTcThreads, smem, st>>>(tmX, tmDY, p);                                  \
+    sc::launch_pdl((tc_conv_wgrad_kernel<KC>), grid, kTcThreads, smem, st, tmX, tmDY, p);                                  \
     if (p.ksplit > 1) {                                                                                      \
-      const int64_t total4 = (int64_t)p.m_blocks * p.n_blocks * 32 * p.block_n;                              \
-      int64_t rb = (total4 + 255) / 256;                                                                     \
-      if (rb > kNumSMs * 8) rb = kNumSMs * 8;                                                                \
-      tc_wgrad_reduce_kernel<KC><<<(int)rb, 256, 0, st>>>(p);                                                \
+      const int items = p.cchunks * (KC / kWredT) * ((p.Cout + kWredT - 1) / kWredT);                      \
+      sc::launch_pdl((tc_wgrad_reduce_kernel<KC>), items, 256, 0, st, p);                                   \
     }                                                                                                        \
   } while (0)
   if (kc == 64) LAUNCH_WGRAD(64);

@@ -66,6 +66,7 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 
 __global__ void __launch_bounds__(kThreads, 2)
 tc_conv3x3_halo_kernel(HaloParams p) {
+  sc::pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem[];
   const int np = p.np;
   const int B_BYTES = 9 * np * p.Cout * 16;                         // [tap*np + plane][Cout] granules
@@ -441,6 +442,6 @@ extern "C" int sc_tc_conv3x3_halo(const void* x, int ldx, const void* w_bf16, vo
       return SC_ERR_CUDA;
     }
   }
-  tc_conv3x3_halo_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  sc::launch_pdl((tc_conv3x3_halo_kernel), grid, kThreads, smem, (cudaStream_t)stream, p);
   return check_launch();
 }

@@ -57,6 +57,7 @@ struct Geo {
 template <int GW>
 __global__ void __launch_bounds__(kThreads, 2)
 tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, WgHaloParams p) {
+  sc::pdl_wait();
   using G = Geo<GW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -196,25 +197,39 @@ tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   }
 }
 
-// dW[co][ci][kh][kw] += sum over CTAs (in CTA order) of partial[cta][g][kh][kw][ci_local][co]
+// dW[co][ci][kh][kw] += sum over CTAs of partial[cta][g][kh][kw][ci_local][co], in a FIXED order: warp w of the block sums
+// the rows r = w, w + 32, ... (coalesced 128-byte reads of 32 neighbouring elements), warp 0 then adds the 32 slice sums
+// in slice order.  (One thread per element walking all ~300 rows serially was latency-bound: 63 us for 2304 elements.)
 template <int GW>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 wgrad_halo_reduce_kernel(const float* __restrict__ partials, int nrows, int ng, int Cin, int Cout, float* __restrict__ dw) {
+  sc::pdl_wait();
+  __shared__ float slice[32][33];
   const int per = ng * 9 * GW * Cout;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < per; e += gridDim.x * blockDim.x) {
-    const int co = e % Cout;
-    int t = e / Cout;
-    const int cil = t % GW;
-    t /= GW;
-    const int kw = t % 3;
-    t /= 3;
-    const int kh = t % 3;
-    const int g = t / 3;
-    const int ci = g * GW + cil;
-    if (ci >= Cin) continue;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int e0 = blockIdx.x * 32; e0 < per; e0 += gridDim.x * 32) {
+    const int e = e0 + lane;
     float s = 0.f;
-    for (int r = 0; r < nrows; ++r) s += __ldcg(partials + (size_t)r * per + e);     // fixed order
-    dw[((size_t)co * Cin + ci) * 9 + kh * 3 + kw] += s;
+    if (e < per)
+      for (int r = w; r < nrows; r += 32) s += __ldcg(partials + (size_t)r * per + e);
+    slice[w][lane] = s;
+    __syncthreads();
+    if (w == 0 && e < per) {
+      float t = slice[0][lane];
+#pragma unroll
+      for (int k = 1; k < 32; ++k) t += slice[k][lane];
+      const int co = e % Cout;
+      int q = e / Cout;
+      const int cil = q % GW;
+      q /= GW;
+      const int kw = q % 3;
+      q /= 3;
+      const int kh = q % 3;
+      const int g = q / 3;
+      const int ci = g * GW + cil;
+      if (ci < Cin) dw[((size_t)co * Cin + ci) * 9 + kh * 3 + kw] += t;
+    }
+    __syncthreads();
   }
 }
 
@@ -299,18 +314,18 @@ extern "C" int sc_tc_wgrad_halo(const void* x, int ldx, const void* dy, int lddy
   const size_t smem = (size_t)pl.stages * pl.stage_bytes + 1024 + 256;
   cudaStream_t st = (cudaStream_t)stream;
   const int per = pl.ng * 9 * pl.gw * Cout;
-  const int rblocks = (per + 255) / 256;
+  const int rblocks = (per + 31) / 32;
   cudaError_t e;
   if (pl.gw == 16) {
     e = cudaFuncSetAttribute(tc_wgrad_halo_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
-    tc_wgrad_halo_kernel<16><<<pl.grid, kThreads, smem, st>>>(tmX, tmDY, p);
-    wgrad_halo_reduce_kernel<16><<<rblocks, 256, 0, st>>>(partials, pl.grid, pl.ng, Cin, Cout, dw_oihw);
+    sc::launch_pdl((tc_wgrad_halo_kernel<16>), pl.grid, kThreads, smem, st, tmX, tmDY, p);
+    sc::launch_pdl((wgrad_halo_reduce_kernel<16>), rblocks, 1024, 0, st, partials, pl.grid, pl.ng, Cin, Cout, dw_oihw);
   } else {
     e = cudaFuncSetAttribute(tc_wgrad_halo_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
-    tc_wgrad_halo_kernel<32><<<pl.grid, kThreads, smem, st>>>(tmX, tmDY, p);
-    wgrad_halo_reduce_kernel<32><<<rblocks, 256, 0, st>>>(partials, pl.grid, pl.ng, Cin, Cout, dw_oihw);
+    sc::launch_pdl((tc_wgrad_halo_kernel<32>), pl.grid, kThreads, smem, st, tmX, tmDY, p);
+    sc::launch_pdl((wgrad_halo_reduce_kernel<32>), rblocks, 1024, 0, st, partials, pl.grid, pl.ng, Cin, Cout, dw_oihw);
   }
   return check_launch();
 }

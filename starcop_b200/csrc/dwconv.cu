@@ -123,6 +123,7 @@ dw_fprop_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict
                 const float* __restrict__ shift, int act, const float* __restrict__ w, int mirror, T* __restrict__ y,
                 int ldy, double* __restrict__ stats, int H, int W, int C, int Ho, int Wo, DwTiles g, int ns,
                 int stage_bytes) {
+  sc::pdl_wait();
   constexpr int TWP = S == 1 ? 4 : 2;
   using G = DwGeo<S, CVB, TWP>;
   constexpr int NI = (TWP - 1) * S + 3;
@@ -274,6 +275,7 @@ template <typename T, int CVB>
 __global__ void __launch_bounds__(kDwThreads, 3)
 dw_dgrad_s2_kernel(const __grid_constant__ CUtensorMap tmDY, const float* __restrict__ w, T* __restrict__ dx, int lddx,
                    int H, int W, int C, DwTiles g, int ns, int stage_bytes) {
+  sc::pdl_wait();
   using G = DwGeoD2<CVB>;
   constexpr int IW = G::IW;
   constexpr uint32_t kTileBytes = G::TILE_ELEMS * sizeof(T);
@@ -370,6 +372,7 @@ __global__ void __launch_bounds__(kDwThreads, 2)
 dw_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
                 const float* __restrict__ scale, const float* __restrict__ shift, int act, float* __restrict__ partial,
                 int H, int W, int C, DwTiles g, int ns, int stage_bytes) {
+  sc::pdl_wait();
   constexpr int TWP = 2;
   using G = DwGeo<S, CVB, TWP>;
   constexpr int NI = (TWP - 1) * S + 3;
@@ -482,6 +485,7 @@ template <typename T, int CVB>
 __global__ void __launch_bounds__(kDwThreads, 2)
 head_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ dl, float* __restrict__ partial,
                        int H, int W, int C, DwTiles g, int ns, int stage_bytes) {
+  sc::pdl_wait();
   constexpr int TWP = 2;
   using G = DwGeo<1, CVB, TWP>;
   constexpr int NI = TWP + 2;
@@ -584,6 +588,7 @@ head_wgrad_tile_kernel(const __grid_constant__ CUtensorMap tmX, const float* __r
 
 __global__ void head_wgrad_sum_kernel(const float* __restrict__ partial, int nrows, int n, float* __restrict__ dw,
                                       float* __restrict__ dbias) {
+  sc::pdl_wait();
   __shared__ float sh[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = blockIdx.x * 32 + tx;
@@ -600,6 +605,7 @@ __global__ void head_wgrad_sum_kernel(const float* __restrict__ partial, int nro
 }
 
 __global__ void dw_wgrad_sum_kernel(const float* __restrict__ partial, int nrows, int n, float* __restrict__ dw) {
+  sc::pdl_wait();
   __shared__ float sh[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int i = blockIdx.x * 32 + tx;
@@ -619,6 +625,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 dw_dgrad_generic_kernel(const T* __restrict__ dy, int lddy, const float* __restrict__ w, T* __restrict__ dx, int lddx,
                         int N, int H, int W, int C, int stride, int Ho, int Wo) {
+  sc::pdl_wait();
   int CV = C / 8;
   int64_t total = (int64_t)N * H * W * CV;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -723,7 +730,7 @@ static int launch_fprop_cvb(const T* x, int ldx, const float* scale, const float
   if (!encode_nhwc_plain(&tmX, x, (int)sizeof(T), C, W, H, N, ldx, CVB * 8, G::IW, G::IH)) return SC_ERR_NO_DEVICE;
   int rc = set_smem(dw_fprop_kernel<T, S, CVB>, smem);
   if (rc != SC_OK) return rc;
-  dw_fprop_kernel<T, S, CVB><<<dim3(gx, n_cb), kDwThreads, smem, st>>>(tmX, scale, shift, act, w, mirror, y, ldy, stats, H,
+  sc::launch_pdl((dw_fprop_kernel<T, S, CVB>), dim3(gx, n_cb), kDwThreads, smem, st, tmX, scale, shift, act, w, mirror, y, ldy, stats, H,
                                                                        W, C, Ho, Wo, g, ns, (int)stage);
   return check_launch();
 }
@@ -748,7 +755,7 @@ static int launch_dgrad_s2_cvb(const T* dy, int lddy, const float* w, T* dx, int
   if (!encode_nhwc_plain(&tmDY, dy, (int)sizeof(T), C, Wo, Ho, N, lddy, CVB * 8, G::IW, G::IH)) return SC_ERR_NO_DEVICE;
   int rc = set_smem(dw_dgrad_s2_kernel<T, CVB>, smem);
   if (rc != SC_OK) return rc;
-  dw_dgrad_s2_kernel<T, CVB><<<dim3(gx, n_cb), kDwThreads, smem, st>>>(tmDY, w, dx, lddx, H, W, C, g, ns, (int)stage);
+  sc::launch_pdl((dw_dgrad_s2_kernel<T, CVB>), dim3(gx, n_cb), kDwThreads, smem, st, tmDY, w, dx, lddx, H, W, C, g, ns, (int)stage);
   return check_launch();
 }
 
@@ -776,7 +783,7 @@ static int launch_wgrad_cvb(const T* x, int ldx, const float* scale, const float
     return SC_ERR_NO_DEVICE;
   int rc = set_smem(dw_wgrad_kernel<T, S, CVB>, smem);
   if (rc != SC_OK) return rc;
-  dw_wgrad_kernel<T, S, CVB><<<dim3(gx, n_cb), kDwThreads, smem, st>>>(tmX, tmDY, scale, shift, act, workspace, H, W, C, g,
+  sc::launch_pdl((dw_wgrad_kernel<T, S, CVB>), dim3(gx, n_cb), kDwThreads, smem, st, tmX, tmDY, scale, shift, act, workspace, H, W, C, g,
                                                                        ns, (int)stage);
   return check_launch();
 }
@@ -797,10 +804,10 @@ static int launch_head_wgrad_cvb(const T* x, int ldx, const float* dl, float* dw
   if (!encode_nhwc_plain(&tmX, x, (int)sizeof(T), C, W, H, N, ldx, CVB * 8, G::IW, G::IH)) return SC_ERR_NO_DEVICE;
   int rc = set_smem(head_wgrad_tile_kernel<T, CVB>, smem);
   if (rc != SC_OK) return rc;
-  head_wgrad_tile_kernel<T, CVB><<<gx, kDwThreads, smem, st>>>(tmX, dl, workspace, H, W, C, g, ns, (int)stage);
+  sc::launch_pdl((head_wgrad_tile_kernel<T, CVB>), gx, kDwThreads, smem, st, tmX, dl, workspace, H, W, C, g, ns, (int)stage);
   rc = check_launch();
   if (rc != SC_OK) return rc;
-  head_wgrad_sum_kernel<<<(C * 9 + 1 + 31) / 32, dim3(32, 32), 0, st>>>(workspace, gx, C * 9, dw, dbias);
+  sc::launch_pdl((head_wgrad_sum_kernel), (C * 9 + 1 + 31) / 32, dim3(32, 32), 0, st, workspace, gx, C * 9, dw, dbias);
   return check_launch();
 }
 
@@ -877,7 +884,7 @@ extern "C" int sc_dwconv_dgrad(const void* dy, int lddy, const float* w, void* d
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
     int64_t total = (int64_t)N * H * W * (C / 8);
     int64_t b = (total + 255) / 256, cap = (int64_t)kNumSMs * 8;
-    SC_DISPATCH_DTYPE(dtype, (dw_dgrad_generic_kernel<T><<<(int)(b < cap ? b : cap), 256, 0, st>>>(
+    SC_DISPATCH_DTYPE(dtype, (sc::launch_pdl((dw_dgrad_generic_kernel<T>), (int)(b < cap ? b : cap), 256, 0, st, 
                                  (const T*)dy, lddy, w, (T*)dx, lddx, N, H, W, C, stride, Ho, Wo)));
     return check_launch();
   }
@@ -910,6 +917,6 @@ extern "C" int sc_dwconv_wgrad(const void* x, int ldx, const float* scale, const
   SC_DISPATCH_DTYPE(dtype, rc = launch_wgrad<T>((const T*)x, ldx, scale, shift, act, (const T*)dy, lddy, workspace, &rows,
                                                 N, H, W, C, stride, st));
   if (rc != SC_OK) return rc;
-  dw_wgrad_sum_kernel<<<(C * 9 + 31) / 32, dim3(32, 32), 0, st>>>(workspace, rows, C * 9, dw);
+  sc::launch_pdl((dw_wgrad_sum_kernel), (C * 9 + 31) / 32, dim3(32, 32), 0, st, workspace, rows, C * 9, dw);
   return check_launch();
 }

@@ -8,6 +8,13 @@
 
 namespace sc {
 thread_local cudaError_t g_last_error = cudaSuccess;
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("STARCOP_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 }
 using namespace sc;
 
@@ -23,6 +30,7 @@ __global__ void normalize_pack_kernel(const float* __restrict__ x, const double*
                                       const double* __restrict__ hi, int f64_path, int C, int64_t HW,
                                       int64_t total_px, T* __restrict__ out_nhwc, int ld_out,
                                       float* __restrict__ out_nchw) {
+  sc::pdl_wait();
   // one thread per pixel: NCHW reads are coalesced per channel plane, NHWC writes are ld_out wide
   for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < total_px;
        p += (int64_t)gridDim.x * blockDim.x) {
@@ -56,7 +64,7 @@ extern "C" int sc_normalize_pack(const float* x, const double* off, const double
   int64_t HW = (int64_t)H * W, total = HW * B;
   int blocks = (int)((total + 255) / 256);
   if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
-  SC_DISPATCH_DTYPE(dtype, (normalize_pack_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+  SC_DISPATCH_DTYPE(dtype, (sc::launch_pdl((normalize_pack_kernel<T>), blocks, 256, 0, (cudaStream_t)stream, 
                                x, off, fac, lo, hi, f64_path, C, HW, total, (T*)out_nhwc, ld_out, out_nchw)));
   return check_launch();
 }
@@ -89,6 +97,7 @@ static int red_blocks(int64_t P, int PL, int gy) {
 template <typename T>
 __global__ void bn_stats_kernel(const T* __restrict__ y, int ldy, double* __restrict__ partials, int64_t P,
                                 int C, int CVB, int PL) {
+  sc::pdl_wait();
   extern __shared__ double sm[];   // [PL][CVB][16]
   int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
   int cv = blockIdx.y * CVB + cvl;
@@ -174,7 +183,7 @@ extern "C" int sc_bn_stats(const void* y, int ldy, double* partials, int* nrows_
   dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
   *nrows_host = (int)grid.x;
   size_t smem = (size_t)g.PL * g.CVB * 16 * sizeof(double);   // <= 32 KB
-  SC_DISPATCH_DTYPE(dtype, (bn_stats_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  SC_DISPATCH_DTYPE(dtype, (sc::launch_pdl((bn_stats_kernel<T>), grid, 256, smem, (cudaStream_t)stream, 
                                (const T*)y, ldy, partials, P, C, g.CVB, g.PL)));
   return check_launch();
 }
@@ -188,6 +197,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partials, int nrow
                                    float* running_mean, float* running_var, float momentum, float eps,
                                    int training, float* scale, float* shift, float* save_mean,
                                    float* save_invstd) {
+  sc::pdl_wait();
   __shared__ double sh[2][kRedY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
@@ -249,7 +259,7 @@ extern "C" int sc_bn_finalize(const double* sums, int nrows, int64_t P, int C, c
   if (C <= 0 || !scale || !shift || (training && (!sums || nrows > SC_BN_MAX_PARTIALS)) ||
       (!training && (!running_mean || !running_var)))
     return SC_ERR_BAD_ARG;
-  bn_finalize_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, (cudaStream_t)stream>>>(
+  sc::launch_pdl((bn_finalize_kernel), (C + 31) / 32, dim3(32, kRedY), 0, (cudaStream_t)stream, 
       sums, nrows, P, C, gamma, beta, running_mean, running_var, momentum, eps, training, scale, shift,
       save_mean, save_invstd);
   return check_launch();
@@ -260,6 +270,7 @@ __global__ void __launch_bounds__(256)
 bn_act_kernel(const T* __restrict__ y, int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
               int act, const T* __restrict__ res, int ldr, T* __restrict__ z, int ldz, int64_t P, int C, int H,
               int W, int up2, int CVB, int PL) {
+  sc::pdl_wait();
   const int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
   const int cv = blockIdx.y * CVB + cvl;
   if (pl >= PL || cv * 8 >= C) return;
@@ -316,7 +327,7 @@ extern "C" int sc_bn_act(const void* y, int ldy, const float* scale, const float
   int64_t cap = (kNumSMs * 8) / g.gy;
   if (cap < 1) cap = 1;
   dim3 grid((unsigned)(want < cap ? (want < 1 ? 1 : want) : cap), g.gy);
-  SC_DISPATCH_DTYPE(dtype, (bn_act_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  SC_DISPATCH_DTYPE(dtype, (sc::launch_pdl((bn_act_kernel<T>), grid, 256, 0, (cudaStream_t)stream, 
                                (const T*)y, ldy, scale, shift, act, (const T*)residual, ldr, (T*)z, ldz, P, C, H, W,
                                upsample2, g.CVB, g.PL)));
   return check_launch();
@@ -344,6 +355,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(const T* __restri
                                      int ldy, const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, int act,
                                      double* __restrict__ partials, int64_t P, int C, int H, int W, int CVB, int PL) {
+  sc::pdl_wait();
   extern __shared__ double sm[];   // [PL][CVB][16]
   int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
   int cv = blockIdx.y * CVB + cvl;
@@ -433,6 +445,7 @@ __global__ void __launch_bounds__(kFlatThreads, 2)
 bn_bwd_reduce_flat_kernel(const T* __restrict__ dz, const T* __restrict__ y, const float* __restrict__ scale,
                           const float* __restrict__ shift, const float* __restrict__ mean,
                           const float* __restrict__ invstd, int act, double* __restrict__ partials, int64_t P, int C) {
+  sc::pdl_wait();
   extern __shared__ __align__(128) uint8_t fsm[];
   const int CV = C / 8, PL = kFlatThreads / CV;
   const int PPC = PL * kFlatPixPerThread;                         // pixels per chunk
@@ -528,6 +541,7 @@ bn_bwd_reduce_flat_kernel(const T* __restrict__ dz, const T* __restrict__ y, con
 template <typename T>
 __global__ void __launch_bounds__(kFlatThreads, 2)
 bn_stats_flat_kernel(const T* __restrict__ y, double* __restrict__ partials, int64_t P, int C) {
+  sc::pdl_wait();
   extern __shared__ __align__(128) uint8_t fsm[];
   const int CV = C / 8, PL = kFlatThreads / CV;
   const int PPC = PL * 2 * kFlatPixPerThread;                     // pixels per chunk (one tensor: twice the pixels)
@@ -621,7 +635,7 @@ static int launch_bn_stats_flat(const void* y, double* partials, int* nrows_host
     g_last_error = e;
     return SC_ERR_CUDA;
   }
-  bn_stats_flat_kernel<T><<<gx, kFlatThreads, smem, st>>>((const T*)y, partials, P, C);
+  sc::launch_pdl((bn_stats_flat_kernel<T>), gx, kFlatThreads, smem, st, (const T*)y, partials, P, C);
   return check_launch();
 }
 int bn_stats_flat(const void* y, double* partials, int* nrows_host, int64_t P, int C, int dtype, cudaStream_t st) {
@@ -647,12 +661,12 @@ extern "C" int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void
     if (dtype == SC_F32) {
       e = cudaFuncSetAttribute(bn_bwd_reduce_flat_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
-      bn_bwd_reduce_flat_kernel<float><<<gx, kFlatThreads, smem, (cudaStream_t)stream>>>(
+      sc::launch_pdl((bn_bwd_reduce_flat_kernel<float>), gx, kFlatThreads, smem, (cudaStream_t)stream, 
           (const float*)dz, (const float*)y, scale, shift, mean, invstd, act, red, P, C);
     } else if (dtype == SC_BF16) {
       e = cudaFuncSetAttribute(bn_bwd_reduce_flat_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }
-      bn_bwd_reduce_flat_kernel<__nv_bfloat16><<<gx, kFlatThreads, smem, (cudaStream_t)stream>>>(
+      sc::launch_pdl((bn_bwd_reduce_flat_kernel<__nv_bfloat16>), gx, kFlatThreads, smem, (cudaStream_t)stream, 
           (const __nv_bfloat16*)dz, (const __nv_bfloat16*)y, scale, shift, mean, invstd, act, red, P, C);
     } else {
       return SC_ERR_BAD_ARG;
@@ -663,7 +677,7 @@ extern "C" int sc_bn_bwd_reduce(const void* dz, int lddz, int pooled, const void
   dim3 grid(red_blocks(P, g.PL, g.gy), g.gy);
   *nrows_host = (int)grid.x;
   size_t smem = (size_t)g.PL * g.CVB * 16 * sizeof(double);   // <= 32 KB
-  SC_DISPATCH_DTYPE(dtype, (bn_bwd_reduce_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(
+  SC_DISPATCH_DTYPE(dtype, (sc::launch_pdl((bn_bwd_reduce_kernel<T>), grid, 256, smem, (cudaStream_t)stream, 
                                (const T*)dz, lddz, pooled, (const T*)y, ldy, scale, shift, mean, invstd, act,
                                red, P, C, H, W, g.CVB, g.PL)));
   return check_launch();
@@ -678,6 +692,7 @@ __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const T* __restrict__ dz, int lddz, int pooled, const T* __restrict__ y, int ldy,
                     const float* __restrict__ coef, int act, T* __restrict__ dy, int lddy, int64_t P, int C,
                     int H, int W, int CVB, int PL) {
+  sc::pdl_wait();
   const int cvl = threadIdx.x % CVB, pl = threadIdx.x / CVB;
   const int cv = blockIdx.y * CVB + cvl;
   if (pl >= PL || cv * 8 >= C) return;
@@ -702,6 +717,7 @@ __global__ void bn_bwd_totals_kernel(double* __restrict__ partials, int nrows, i
                                      const float* __restrict__ scale, const float* __restrict__ shift,
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      float* dgamma, float* dbeta, float* __restrict__ coef) {
+  sc::pdl_wait();
   __shared__ double sh[2][kRedY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
@@ -755,14 +771,14 @@ extern "C" int sc_bn_bwd_apply(const void* dz, int lddz, int pooled, const void*
   int64_t P = (int64_t)N * H * W;
   // the coefficient table lives right after the totals row of the partials buffer (4*C floats = 2*C doubles)
   float* coef = reinterpret_cast<float*>(partials + ((int64_t)nrows + 1) * 2 * C);
-  bn_bwd_totals_kernel<<<(C + 31) / 32, dim3(32, kRedY), 0, (cudaStream_t)stream>>>(
+  sc::launch_pdl((bn_bwd_totals_kernel), (C + 31) / 32, dim3(32, kRedY), 0, (cudaStream_t)stream, 
       partials, nrows, C, 1.0 / (double)P, scale, shift, mean, invstd, dgamma, dbeta, coef);
   RedGeom g = red_geom(C);
   int64_t want = (P + g.PL * 4 - 1) / (g.PL * 4);
   int64_t cap = (kNumSMs * 8) / g.gy;
   if (cap < 1) cap = 1;
   dim3 grid((unsigned)(want < cap ? (want < 1 ? 1 : want) : cap), g.gy);
-  SC_DISPATCH_DTYPE(dtype, (bn_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>(
+  SC_DISPATCH_DTYPE(dtype, (sc::launch_pdl((bn_bwd_apply_kernel<T>), grid, 256, 0, (cudaStream_t)stream, 
                                (const T*)dz, lddz, pooled, (const T*)y, ldy, coef, act, (T*)dy, lddy, P, C, H, W,
                                g.CVB, g.PL)));
   return check_launch();
@@ -771,6 +787,7 @@ extern "C" int sc_bn_bwd_apply(const void* dz, int lddz, int pooled, const void*
 template <typename T>
 __global__ void add_into_kernel(const T* __restrict__ a, int lda, int pooled, T* __restrict__ out, int ldo,
                                 int accumulate, int64_t total, int CV, int H, int W) {
+  sc::pdl_wait();
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     int cv = (int)(idx % CV);
@@ -790,7 +807,7 @@ extern "C" int sc_add_into(const void* a, int lda, int pooled, void* out, int ld
   if (!a || !out || C % 8 || lda % 8 || ldo % 8) return SC_ERR_BAD_ARG;
   int CV = C / 8;
   int64_t total = (int64_t)N * H * W * CV;
-  SC_DISPATCH_DTYPE(dtype, (add_into_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  SC_DISPATCH_DTYPE(dtype, (sc::launch_pdl((add_into_kernel<T>), ew_blocks(total), 256, 0, (cudaStream_t)stream, 
                                (const T*)a, lda, pooled, (T*)out, ldo, accumulate, total, CV, H, W)));
   return check_launch();
 }
@@ -804,6 +821,7 @@ template <typename T>
 __global__ void head_fprop_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ w,
                                   const float* __restrict__ bias, float* __restrict__ logits, int N, int H,
                                   int W, int C) {
+  sc::pdl_wait();
   __shared__ float ws[9 * kHeadMaxC];   // [tap][c]
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
     int tap = i / C, c = i % C;
@@ -843,7 +861,7 @@ extern "C" int sc_head_fprop(const void* x, int ldx, const float* w, const float
                              int H, int W, int C, int dtype, void* stream) {
   if (!x || !w || !logits || C % 8 || C > kHeadMaxC || ldx % 8) return SC_ERR_BAD_ARG;
   int64_t total = (int64_t)N * H * W;
-  SC_DISPATCH_DTYPE(dtype, (head_fprop_kernel<T><<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(
+  SC_DISPATCH_DTYPE(dtype, (sc::launch_pdl((head_fprop_kernel<T>), ew_blocks(total), 256, 0, (cudaStream_t)stream, 
                                (const T*)x, ldx, w, bias, logits, N, H, W, C)));
   return check_launch();
 }
@@ -851,6 +869,7 @@ extern "C" int sc_head_fprop(const void* x, int ldx, const float* w, const float
 template <typename T>
 __global__ void head_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dl, T* __restrict__ dx,
                                   int lddx, int N, int H, int W, int C) {
+  sc::pdl_wait();
   __shared__ float ws[9 * kHeadMaxC];
   for (int i = threadIdx.x; i < 9 * C; i += blockDim.x) {
     int tap = i / C, c = i % C;
@@ -891,7 +910,7 @@ extern "C" int sc_head_bwd(const void* x, int ldx, const float* w, const float* 
   if (!x || !w || !dlogits || !dx || C % 8 || C > kHeadMaxC || ldx % 8 || lddx % 8) return SC_ERR_BAD_ARG;
   int64_t total = (int64_t)N * H * W;
   cudaStream_t st = (cudaStream_t)stream;
-  SC_DISPATCH_DTYPE(dtype, (head_dgrad_kernel<T><<<ew_blocks(total), 256, 0, st>>>(w, dlogits, (T*)dx, lddx, N, H, W, C)));
+  SC_DISPATCH_DTYPE(dtype, (sc::launch_pdl((head_dgrad_kernel<T>), ew_blocks(total), 256, 0, st, w, dlogits, (T*)dx, lddx, N, H, W, C)));
   return check_launch();
 }
 
@@ -904,6 +923,7 @@ __global__ void bce_fused_kernel(const float* __restrict__ logits, const float* 
                                  long long* cm_sig, long long* pred_count_sig, float* __restrict__ prediction,
                                  float* __restrict__ loss_px, float* __restrict__ loss_px_w,
                                  long long* __restrict__ pred_binary, long long* __restrict__ differences) {
+  sc::pdl_wait();
   int b = blockIdx.y;
   const int64_t base = (int64_t)b * HW;
   double lsum = 0.0;
@@ -1011,7 +1031,7 @@ extern "C" int sc_bce_fused(const float* logits, const float* y, const float* w,
                             float* loss_px, float* loss_px_w, int64_t* pred_binary, int64_t* differences,
                             void* stream) {
   if (!logits || !y || B <= 0 || HW <= 0 || B > 65535) return SC_ERR_BAD_ARG;
-  bce_fused_kernel<<<bce_grid(B, HW), 256, 0, (cudaStream_t)stream>>>(
+  sc::launch_pdl((bce_fused_kernel), bce_grid(B, HW), 256, 0, (cudaStream_t)stream, 
       logits, y, w, pos_weight, HW, grad_scale, loss_sum, grad, (long long*)cm, (long long*)pred_count,
       (long long*)cm_sig, (long long*)pred_count_sig, prediction, loss_px, loss_px_w, (long long*)pred_binary,
       (long long*)differences);
@@ -1046,10 +1066,12 @@ extern "C" int sc_adam_step(float* p, const float* g, float* m, float* v, int64_
 }
 
 // device-resident step counter and learning rate: the whole train step can be replayed as a CUDA graph
-__global__ void adam_step_inc_kernel(int* step) { *step += 1; }
+__global__ void adam_step_inc_kernel(int* step) {
+  sc::pdl_wait(); *step += 1; }
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, int64_t n, const float* __restrict__ lr_dev, float b1, float b2,
                                 float eps, const int* __restrict__ step_dev, float gs) {
+  sc::pdl_wait();
   const double t = (double)*step_dev;
   const float bc1 = (float)(1.0 - pow((double)b1, t));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
@@ -1068,8 +1090,8 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 extern "C" int sc_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev,
                                 float beta1, float beta2, float eps, int* step_dev, float grad_scale, void* stream) {
   if (!p || !g || !m || !v || !lr_dev || !step_dev || n <= 0) return SC_ERR_BAD_ARG;
-  adam_step_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
-  adam_dev_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr_dev, beta1, beta2, eps, step_dev,
+  sc::launch_pdl((adam_step_inc_kernel), 1, 1, 0, (cudaStream_t)stream, step_dev);
+  sc::launch_pdl((adam_dev_kernel), ew_blocks(n), 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr_dev, beta1, beta2, eps, step_dev,
                                                                    grad_scale);
   return check_launch();
 }

@@ -546,7 +546,12 @@ ratio_cluster16_kernel(const float* __restrict__ bg, const float* __restrict__ s
       const int band = o >> 10, q = (o >> 8) & 3, b = o & 255;
       unsigned int t = 0;
       if (uq[band][q] == q) {
-        for (int r = 0; r < csize; ++r) t += cluster.map_shared_rank(&hist[pp][band][q][b], r)[0];
+        // all remote loads in flight together (one DSMEM latency, not csize of them), summed in rank order
+        unsigned int v[kC16];
+#pragma unroll
+        for (int r = 0; r < kC16; ++r) v[r] = r < csize ? cluster.map_shared_rank(&hist[pp][band][q][b], r)[0] : 0u;
+#pragma unroll
+        for (int r = 0; r < kC16; ++r) t += v[r];
       }
       tot[band][q][b] = t;
     }
