@@ -520,17 +520,23 @@ struct WgradParams {
   int stages;
   float* dw;
   float* partials;                 // [m_blocks * n_blocks][ksplit][128][block_n] fp32 (ksplit > 1)
+  int red_items, red_groups;       // split reduction: blocks of the gradient x groups of splits (one CTA each)
+  float* red_scratch;              // [red_items][red_groups][64 * KH * KW] group sums (red_groups > 1)
+  int* red_tickets;                // [red_items] arrival counters, cleared by the wgrad kernel itself
 };
 
 // dW += sum over the pixel splits of their partial tiles, in a fixed order (deterministic).  The partial tiles hold the
-// gradient as [tap, ci][co] (co fastest), the OIHW gradient wants [co][ci][tap].  One CTA owns the block
-// (all taps) x (8 input channels) x (8 output channels): it gathers the block with 32-byte row reads (one full sector
-// each), transposes it through shared memory and writes each output channel's 8 * KH * KW contiguous floats.  The
-// splits (up to ~300 for the thin high-resolution layers) are summed in `slices` interleaved slices by different
-// threads -- split k belongs to slice k % slices -- and the slice sums are added in slice order, so the result does not
-// depend on scheduling.  Small blocks keep the grid large: 64 -> 64 3x3 is 64 CTAs, 1376 -> 256 3x3 is 5632.
-// (One scattered 4-byte read-modify-write per element cost 73 us on the 1376 -> 256 layer; one thread per element
-// walking all splits serially cost 46 us on a 16 x 96 weight.)
+// gradient as [tap, ci][co] (co fastest), the OIHW gradient wants [co][ci][tap].  The gradient is cut into blocks of
+// (all taps) x (8 input channels) x (8 output channels); the splits of a block (up to ~300 for the thin
+// high-resolution layers) are cut into `red_groups` contiguous groups and ONE CTA sums one group of one block:
+//   * inside the CTA the group's splits are summed in interleaved slices by different threads (split k of the group
+//     belongs to slice k % slices; four loads in flight per thread) and the slice sums are added in slice order;
+//   * with one group the CTA transposes the block through shared memory and adds it into dW with coalesced runs of
+//     8 * KH * KW floats per output channel;
+//   * with several groups it stores its group sum, takes a ticket, and the CTA that arrives LAST adds the group sums
+//     in group order and writes dW.  Which CTA is last varies, the order of the additions never does.
+// Every level has a fixed association, so the result does not depend on scheduling; the grid stays in the hundreds of
+// CTAs for every layer (64 -> 64 3x3 at 60 splits: 64 blocks x 8 groups; the 4 -> 32 stem at 296 splits: 4 x 37).
 constexpr int kWredT = 8;                        // block edge: 8 input x 8 output channels
 constexpr int kWredSliceFloats = 4096;           // scratch for the slice sums (16 KB)
 template <int KC>
@@ -541,51 +547,86 @@ tc_wgrad_reduce_kernel(WgradParams p) {
   constexpr int CGS = KC / kWredT;               // input-channel groups per chunk
   __shared__ float slice_s[kWredSliceFloats];
   __shared__ float tr_s[kWredT][kWredT * 9 + 1];
+  __shared__ int s_last;
   const int KK = p.KH * p.KW;
   const int E = KK * kWredT * kWredT;            // elements of one block: 64 (1x1) or 576 (3x3)
+  const int G = p.red_groups;
+  const int per_group = (p.ksplit + G - 1) / G;
+  const int co_tiles = (p.Cout + kWredT - 1) / kWredT;
+  const size_t split_stride = (size_t)128 * p.block_n;
+  const int item = blockIdx.x / G, grp = blockIdx.x - item * G;
+  const int ct = item % co_tiles;
+  const int cgi = item / co_tiles;
+  const int chunk = cgi / CGS, cg = cgi - chunk * CGS;
+  const int ci0 = chunk * KC + cg * kWredT;
+  if (ci0 >= p.Cin) return;                      // zero-padded channels of a ragged last chunk (whole block idle)
+  const int co0 = ct * kWredT;
+  const int nb = co0 / p.block_n;                // block_n is a multiple of 16: a block never straddles N blocks
+  const int c0 = co0 - nb * p.block_n;
+  const int k0 = grp * per_group;
+  const int k1 = min(p.ksplit, k0 + per_group);
   int slices = kWredSliceFloats / E;
   slices = slices > 16 ? 16 : slices;
-  if (slices > p.ksplit) slices = p.ksplit;
-  const int co_tiles = (p.Cout + kWredT - 1) / kWredT;
-  const int items = p.cchunks * CGS * co_tiles;
-  const size_t split_stride = (size_t)128 * p.block_n;
-  for (int item = blockIdx.x; item < items; item += gridDim.x) {
-    const int ct = item % co_tiles;
-    const int cgi = item / co_tiles;
-    const int chunk = cgi / CGS, cg = cgi - chunk * CGS;
-    const int ci0 = chunk * KC + cg * kWredT;
-    if (ci0 >= p.Cin) continue;                  // zero-padded channels of a ragged last chunk (block-uniform)
-    const int co0 = ct * kWredT;
-    const int nb = co0 / p.block_n;              // block_n is a multiple of 16: a block never straddles N blocks
-    const int c0 = co0 - nb * p.block_n;
-    for (int idx = threadIdx.x; idx < E * slices; idx += 256) {
-      const int sl = idx / E, e = idx - sl * E;
+  if (slices > k1 - k0) slices = max(k1 - k0, 1);
+  for (int idx = threadIdx.x; idx < E * slices; idx += 256) {
+    const int sl = idx / E, e = idx - sl * E;
+    const int col = e % kWredT;
+    const int t = e / kWredT;
+    const int cil = cg * kWredT + t % kWredT, tap = t / kWredT;
+    const int j = tap * p.cchunks + chunk;
+    const int mb = j / SUBS, sidx = j - mb * SUBS;
+    const float* base = p.partials + (((size_t)(nb * p.m_blocks + mb) * p.ksplit) * 128 + sidx * KC + cil) * p.block_n + c0 + col;
+    float a = 0.f;
+    int k = k0 + sl;
+    for (; k + 3 * slices < k1; k += 4 * slices) {
+      const float x0 = __ldcg(base + (size_t)k * split_stride), x1 = __ldcg(base + (size_t)(k + slices) * split_stride);
+      const float x2 = __ldcg(base + (size_t)(k + 2 * slices) * split_stride), x3 = __ldcg(base + (size_t)(k + 3 * slices) * split_stride);
+      a += x0; a += x1; a += x2; a += x3;
+    }
+    for (; k < k1; k += slices) a += __ldcg(base + (size_t)k * split_stride);
+    slice_s[idx] = a;
+  }
+  __syncthreads();
+  float* mine = p.red_scratch + ((size_t)item * G + grp) * E;
+  for (int e = threadIdx.x; e < E; e += 256) {
+    float a = slice_s[e];
+    for (int sl = 1; sl < slices; ++sl) a += slice_s[sl * E + e];
+    if (G == 1) {
       const int col = e % kWredT;
       const int t = e / kWredT;
-      const int cil = cg * kWredT + t % kWredT, tap = t / kWredT;
-      const int j = tap * p.cchunks + chunk;
-      const int mb = j / SUBS, sidx = j - mb * SUBS;
-      const float* base = p.partials + (((size_t)(nb * p.m_blocks + mb) * p.ksplit) * 128 + sidx * KC + cil) * p.block_n + c0 + col;
-      float a = 0.f;
-      for (int k = sl; k < p.ksplit; k += slices) a += __ldcg(base + (size_t)k * split_stride);
-      slice_s[idx] = a;
+      tr_s[col][(t % kWredT) * KK + t / kWredT] = a;
+    } else {
+      __stcg(mine + e, a);
     }
+  }
+  if (G > 1) {
+    __threadfence();
     __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(p.red_tickets + item, 1) == G - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const float* all = p.red_scratch + (size_t)item * G * E;
     for (int e = threadIdx.x; e < E; e += 256) {
-      float a = slice_s[e];
-      for (int sl = 1; sl < slices; ++sl) a += slice_s[sl * E + e];
+      float a = __ldcg(all + e);
+      int g = 1;
+      for (; g + 3 < G; g += 4) {
+        const float x0 = __ldcg(all + (size_t)g * E + e), x1 = __ldcg(all + (size_t)(g + 1) * E + e);
+        const float x2 = __ldcg(all + (size_t)(g + 2) * E + e), x3 = __ldcg(all + (size_t)(g + 3) * E + e);
+        a += x0; a += x1; a += x2; a += x3;
+      }
+      for (; g < G; ++g) a += __ldcg(all + (size_t)g * E + e);
       const int col = e % kWredT;
       const int t = e / kWredT;
       tr_s[col][(t % kWredT) * KK + t / kWredT] = a;
     }
-    __syncthreads();
-    const int n = min(kWredT, p.Cin - ci0) * KK; // valid contiguous floats per output channel
-    for (int e = threadIdx.x; e < kWredT * n; e += 256) {
-      const int col = e / n, o = e - col * n;
-      const int co = co0 + col;
-      if (co < p.Cout) p.dw[((int64_t)co * p.Cin + ci0) * KK + o] += tr_s[col][o];
-    }
-    __syncthreads();
+  }
+  __syncthreads();
+  const int n = min(kWredT, p.Cin - ci0) * KK;   // valid contiguous floats per output channel
+  for (int e = threadIdx.x; e < kWredT * n; e += 256) {
+    const int col = e / n, o = e - col * n;
+    const int co = co0 + col;
+    if (co < p.Cout) p.dw[((int64_t)co * p.Cin + ci0) * KK + o] += tr_s[col][o];
   }
 }
 
@@ -593,6 +634,8 @@ template <int KC>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, WgradParams p) {
   sc::pdl_wait();
+  if (blockIdx.x == 0 && p.red_groups > 1)       // arrival counters of the split reduction that follows in the stream
+    for (int i = threadIdx.x; i < p.red_items; i += kTcThreads) p.red_tickets[i] = 0;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int PIX = 64;                        // pixels (K) per stage: 4 rows x 16 cols
@@ -785,8 +828,23 @@ static int wgrad_geometry(int N, int Ho, int Wo, int Cin, int Cout, int KH, int 
   // every split must own at least one pixel tile (its partial tile enters the ordered sum)
   const int per = (p->p_tiles + ksplit - 1) / ksplit;
   p->ksplit = (p->p_tiles + per - 1) / per;
+  // split reduction: one CTA per (8 x 8 channel block, group of splits); aim at ~4 CTAs per SM, >= 4 splits per group
+  p->red_items = p->cchunks * (kc / kWredT) * ((Cout + kWredT - 1) / kWredT);
+  int groups = (4 * kNumSMs + p->red_items - 1) / p->red_items;
+  if (groups > (p->ksplit + 3) / 4) groups = (p->ksplit + 3) / 4;
+  if (groups > 32) groups = 32;
+  if (groups < 1) groups = 1;
+  const int per_group = (p->ksplit + groups - 1) / groups;
+  p->red_groups = (p->ksplit + per_group - 1) / per_group;       // no empty group
   *kc_out = kc;
   return SC_OK;
+}
+// workspace layout: [partial tiles][group sums][tickets]
+static size_t wgrad_partials_bytes(const WgradParams& p) {
+  return ((size_t)p.m_blocks * p.n_blocks * p.ksplit * 128 * p.block_n * sizeof(float) + 255) & ~(size_t)255;
+}
+static size_t wgrad_scratch_bytes(const WgradParams& p) {
+  return p.red_groups > 1 ? ((size_t)p.red_items * p.red_groups * 64 * p.KH * p.KW * sizeof(float) + 255) & ~(size_t)255 : 0;
 }
 
 extern "C" int64_t sc_tc_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin, int Cout, int KH, int KW, int stride) {
@@ -797,7 +855,8 @@ extern "C" int64_t sc_tc_conv_wgrad_workspace_bytes(int N, int H, int W, int Cin
   WgradParams p;
   int kc;
   if (Cin < 1 || wgrad_geometry(N, Ho, Wo, Cin, Cout, KH, KW, &p, &kc) != SC_OK) return -1;
-  return p.ksplit > 1 ? (int64_t)p.m_blocks * p.n_blocks * p.ksplit * 128 * p.block_n * sizeof(float) : 0;
+  p.KH = KH; p.KW = KW;
+  return p.ksplit > 1 ? (int64_t)(wgrad_partials_bytes(p) + wgrad_scratch_bytes(p) + (size_t)p.red_items * sizeof(int)) : 0;
 }
 
 extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy, float* dw_oihw, float* partials,
@@ -818,6 +877,8 @@ extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy
   if (p.ksplit > 1 && !partials) return SC_ERR_BAD_ARG;
   p.dw = dw_oihw;
   p.partials = partials;
+  p.red_scratch = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(partials) + wgrad_partials_bytes(p));
+  p.red_tickets = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(p.red_scratch) + wgrad_scratch_bytes(p));
   const int stage_bytes = (64 * 128 * 2 + p.nb_boxes * 64 * p.kcb * 2 + 1023) & ~1023;
   const int tail = 1024 + 256;
   int stages = (200 * 1024 - tail) / stage_bytes;
@@ -840,8 +901,7 @@ extern "C" int sc_tc_conv_wgrad(const void* x, int ldx, const void* dy, int lddy
     if (e != cudaSuccess) { g_last_error = e; return SC_ERR_CUDA; }                                          \
     sc::launch_pdl((tc_conv_wgrad_kernel<KC>), grid, kTcThreads, smem, st, tmX, tmDY, p);                                  \
     if (p.ksplit > 1) {                                                                                      \
-      const int items = p.cchunks * (KC / kWredT) * ((p.Cout + kWredT - 1) / kWredT);                      \
-      sc::launch_pdl((tc_wgrad_reduce_kernel<KC>), items, 256, 0, st, p);                                   \
+      sc::launch_pdl((tc_wgrad_reduce_kernel<KC>), p.red_items * p.red_groups, 256, 0, st, p);              \
     }                                                                                                        \
   } while (0)
   if (kc == 64) LAUNCH_WGRAD(64);

@@ -3,6 +3,8 @@
 // BCE + decisions + confusion counts, Adam.  All NHWC, 8-channel vectors, fp32 math, fp64 sums.
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
