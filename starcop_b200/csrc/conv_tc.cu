@@ -249,6 +249,9 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       const uint32_t idesc = make_idesc_bf16(128, p.block_n, 0, 0);
       constexpr uint32_t LAYOUT = layout_for_row_bytes(ROW_BYTES);
       constexpr uint32_t SBO = 8 * ROW_BYTES;
+      const uint64_t desc0 = make_smem_desc(smem_u32(smem), 16, SBO, LAYOUT);
+      const uint64_t desc_hi = desc0 & 0xffffffff00000000ull;
+      const uint32_t desc_lo0 = (uint32_t)desc0;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -261,13 +264,16 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           const int g_here = min(G, ksteps - si * G);
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          uint32_t aaddr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          uint32_t baddr = aaddr + G * A_BYTES;
+          // descriptors: assembled once (desc0), then a stage / group / K step is an add on the low word (start
+          // address in 16-byte units; shared memory < 256 KB, the 14-bit field never carries) -- the issuing thread
+          // is the limit on the thin layers, every instruction between two MMAs counts
+          const uint32_t a_lo = desc_lo0 + (uint32_t)stage * (uint32_t)(STAGE_BYTES >> 4);
+          const uint32_t b_lo = a_lo + (uint32_t)(G * A_BYTES >> 4);
           for (int g = 0; g < g_here; ++g) {
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
-              uint64_t ad = make_smem_desc(aaddr + g * A_BYTES + k * 32, 16, SBO, LAYOUT);
-              uint64_t bd = make_smem_desc(baddr + g * B_BYTES + k * 32, 16, SBO, LAYOUT);
+              const uint64_t ad = desc_hi | (uint64_t)(a_lo + (uint32_t)(g * (A_BYTES >> 4) + k * 2));
+              const uint64_t bd = desc_hi | (uint64_t)(b_lo + (uint32_t)(g * (B_BYTES >> 4) + k * 2));
               umma_bf16(d_tmem, ad, bd, idesc, (si > 0 || g > 0 || k > 0) ? 1u : 0u);
             }
           }
@@ -308,7 +314,37 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int h = th * 8 + row / 16, w = tw * 16 + row % 16;
       __nv_bfloat16* yp = p.y + (((int64_t)img * p.H + h) * p.W + w) * p.ldy + n0;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (p.tmem_cols / 2);
-      for (int c0 = 0; c0 < p.block_n; c0 += 16) {
+      int c_begin = 0;
+      if (wide_ok && !p.stats) {
+        // store-bound layers (the 1x1 expansions: one MMA per tile, 12-120 KB of output): up to four TMEM loads in
+        // flight behind ONE tcgen05.wait::ld, then the 256-bit stores back to back -- the per-chunk load -> wait ->
+        // store chain cost one TMEM round trip per 16 channels (f2.exp fprop 112 us for 235 MB)
+        const int full = min(p.block_n, (p.Cout - n0) & ~15);       // columns covered by complete 16-channel groups
+        for (; c_begin + 16 <= full; c_begin += 64) {
+          uint32_t r[4][16];
+          const int ng = min(4, (full - c_begin) / 16);
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            if (g < ng) tmem_ld16_nowait(taddr + c_begin + 16 * g, r[g]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (g < ng) {
+              uint32_t w8[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[g][2 * i]), __uint_as_float(r[g][2 * i + 1]));
+                w8[i] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(yp + c_begin + 16 * g), "r"(w8[0]), "r"(w8[1]),
+                           "r"(w8[2]), "r"(w8[3]), "r"(w8[4]), "r"(w8[5]), "r"(w8[6]), "r"(w8[7])
+                           : "memory");
+            }
+          }
+        }
+        c_begin = full;
+      }
+      for (int c0 = c_begin; c0 < p.block_n; c0 += 16) {
         float v[16];
         tmem_ld16(taddr + c0, v);
         if (wide_ok && n0 + c0 + 16 <= p.Cout) {
@@ -734,16 +770,21 @@ tc_conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
       const uint32_t b_sbo = 8 * p.kcb * 2;
       int stage = 0;
       uint32_t phase = 0;
+      // descriptors assembled once; a stage / K step is an add on the low word (start address, 16-byte units)
+      const uint64_t ad0 = make_smem_desc(smem_u32(smem), A_SUB_BYTES, A_SBO, A_LAYOUT);
+      const uint64_t bd0 = make_smem_desc(smem_u32(smem) + A_BYTES, B_BOX_BYTES, b_sbo, b_layout);
+      const uint64_t a_hi = ad0 & 0xffffffff00000000ull, b_hi = bd0 & 0xffffffff00000000ull;
+      const uint32_t a_lo0 = (uint32_t)ad0, b_lo0 = (uint32_t)bd0;
+      const uint32_t b_kstep = (uint32_t)(16 * p.kcb * 2) >> 4;
       for (int i = 0; i < nsteps; ++i) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        uint32_t aaddr = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-        uint32_t baddr = aaddr + A_BYTES;
+        const uint32_t soff = (uint32_t)stage * (uint32_t)(STAGE_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < PIX / 16; ++k) {
           // K advances over pixels: 16 rows of (kc*2) bytes
-          uint64_t ad = make_smem_desc(aaddr + k * 16 * KC * 2, A_SUB_BYTES, A_SBO, A_LAYOUT);
-          uint64_t bd = make_smem_desc(baddr + k * 16 * p.kcb * 2, B_BOX_BYTES, b_sbo, b_layout);
+          const uint64_t ad = a_hi | (uint64_t)(a_lo0 + soff + (uint32_t)(k * 16 * KC * 2 >> 4));
+          const uint64_t bd = b_hi | (uint64_t)(b_lo0 + soff + (uint32_t)k * b_kstep);
           umma_bf16(tmem_base, ad, bd, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty[stage]);

@@ -24,6 +24,8 @@
 //     TMEM accumulators): one tile's K loop is a dependent chain that leaves the pipe idle at N <= 80;
 //   * ALL taps' weights stay resident in shared memory for the CTA's lifetime ([K/8][Cout] granules).
 // Warp roles / TMEM double buffering / BatchNorm statistics epilogue as in conv_tc.cu.
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -32,7 +34,8 @@ using namespace tc;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 256;                         // warps 0-2 gather patches, warp 3 issues the MMAs, warps 4-7 = epilogue
+constexpr int kProducers = 3;
 constexpr int kTileH = 16, kTileW = 8;                 // output tile: M = 128 pixels
 constexpr int kPatchH = kTileH + 2, kPatchW = kTileW + 2;
 constexpr int kPlaneBytes = kPatchH * kPatchW * 16;    // 2880
@@ -87,7 +90,7 @@ tc_conv3x3_halo_kernel(HaloParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&full[i], 32);      // every producer lane publishes its own share of a patch
+      mbar_init(&full[i], 32 * kProducers);      // every producer lane publishes its own share of a patch
       mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -104,7 +107,7 @@ tc_conv3x3_halo_kernel(HaloParams p) {
     tab[g] = make_int2((ph * p.W + pw) * p.ldx + pl * 8,
                        (pl * kPlaneStride + px * 16) | (ph << 15) | (pw << 20) | ((pl * 8 < p.Cin ? 1 : 0) << 24));
   }
-  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  if (warp == kProducers) tmem_alloc(tmem_slot, p.tmem_cols);
   // resident weights: global [n][k8] granules -> shared [k8][n] granules (un-swizzled K-major B operand)
   {
     const int k8n = 9 * np;
@@ -121,8 +124,15 @@ tc_conv3x3_halo_kernel(HaloParams p) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // producer: gather a patch with cp.async; each lane's share is published by the hardware
+  // Register budget: 2 CTAs x 256 threads leave 128 registers per thread at launch; the gather / MMA warps need ~50,
+  // the epilogue (a batch of four tiles' accumulators in flight + their statistics) ~170: the first warpgroup hands
+  // its surplus to the second one.
+  if (warp < 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (warp < kProducers) {
+    // producers: THREE warps gather a patch with cp.async (ncu, one producer warp: that warp was busy 100 % of the
+    // time at ~200 cycles per LDGSTS -- the copies a single warp may have in flight cap the gather, not its issue
+    // rate -- while the epilogue warps idled 42 % waiting for accumulators); each lane's share is published by the hardware
     // (cp.async.mbarrier.arrive.noinc fires when the lane's copies have landed), so up to `stages` patches
     // are in flight and the producer never blocks on its own loads.  (Publishing with wait_group ->
     // fence.proxy.async -> arrive in the producer was measured 1.3-1.45x slower: the blocking wait caps the
@@ -142,13 +152,13 @@ tc_conv3x3_halo_kernel(HaloParams p) {
       if (h0 >= 0 && w0 >= 0 && h0 + kPatchH <= p.H && w0 + kPatchW <= p.W) {
         // interior patch (all but the image border): no per-pixel bounds checks
 #pragma unroll 4
-        for (int g = lane; g < ngran; g += 32) {
+        for (int g = warp * 32 + lane; g < ngran; g += 32 * kProducers) {
           const int2 t = tab[g];
           cp_async16_zfill(dst + (t.y & 0x7fff), base + t.x, (t.y >> 24) ? 16u : 0u);
         }
       } else {
 #pragma unroll 2
-        for (int g = lane; g < ngran; g += 32) {
+        for (int g = warp * 32 + lane; g < ngran; g += 32 * kProducers) {
           const int2 t = tab[g];
           const int ph = (t.y >> 15) & 31, pw = (t.y >> 20) & 15;
           const bool ok = (unsigned)(h0 + ph) < (unsigned)p.H && (unsigned)(w0 + pw) < (unsigned)p.W && (t.y >> 24);
@@ -161,7 +171,7 @@ tc_conv3x3_halo_kernel(HaloParams p) {
         phase ^= 1;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kProducers) {
     if (lane == 0) {
       // Tiles are processed in BATCHES of G with the MMAs of the batch interleaved tap by tap: the K steps of
       // one tile form a dependent accumulation chain, and at N = 16...80 a single chain leaves the tensor pipe
@@ -181,15 +191,22 @@ tc_conv3x3_halo_kernel(HaloParams p) {
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        uint32_t a_base[kMaxBatch];
-        int st_of[kMaxBatch];
-        for (int g = 0; g < gn; ++g) {
-          mbar_wait(&full[stage], phase);
-          st_of[g] = stage;
-          a_base[g] = sA_u32 + (uint32_t)stage * STAGE_BYTES;
-          if (++stage == p.stages) {
-            stage = 0;
-            phase ^= 1;
+        // The issuing thread is the bottleneck of this kernel (ncu: ~250 cycles per MMA with ~45 dependent
+        // instructions each -- descriptor assembly, local-memory batch tables, per-MMA elect / uniform moves), so the
+        // descriptors are assembled ONCE per batch and a tap / K step / tile is an integer add on their low words
+        // (start address field, 16-byte units: shared memory is < 256 KB, the field never carries).
+        uint32_t a_lo[kMaxBatch];
+        int st_first = stage;
+#pragma unroll
+        for (int g = 0; g < kMaxBatch; ++g) {
+          a_lo[g] = 0;
+          if (g < gn) {
+            mbar_wait(&full[stage], phase);
+            a_lo[g] = (uint32_t)make_smem_desc(sA_u32 + (uint32_t)stage * STAGE_BYTES, kPlaneStride, kRowBytes, 0);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
         tc_fence_after();
@@ -197,29 +214,46 @@ tc_conv3x3_halo_kernel(HaloParams p) {
         // (measured: the fence costs < 2 % here)
         fence_proxy_async();
         const uint32_t d_tmem = tmem_base + acc * (G * NP);
-        uint32_t first = 0;
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3, dx = tap - dy * 3;
-          const uint32_t a_off = (dy * kPatchW + dx) * 16;
-          const uint32_t b_tap = baddr + (uint32_t)(tap * np) * b_lbo;
-          for (int kk = 0; kk < kpairs; ++kk) {
-            const uint64_t bd = make_smem_desc(b_tap + 2 * kk * b_lbo, b_lbo, 128, 0);
-            for (int g = 0; g < gn; ++g) {
-              const uint64_t ad = make_smem_desc(a_base[g] + a_off + 2 * kk * kPlaneStride, kPlaneStride, kRowBytes, 0);
-              umma_bf16(d_tmem + g * NP, ad, bd, idesc, first);
+        const uint64_t a_hi = make_smem_desc(0, kPlaneStride, kRowBytes, 0) & 0xffffffff00000000ull;
+        const uint64_t b_desc0 = make_smem_desc(baddr, b_lbo, 128, 0);
+        const uint32_t b_hi32 = (uint32_t)(b_desc0 >> 32), b_lo0 = (uint32_t)b_desc0;
+        const uint32_t b_step = b_lbo >> 4;
+        auto issue = [&](auto gn_c) {
+          constexpr int GN = decltype(gn_c)::value;
+          uint32_t first = 0;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t a_off = (tap / 3) * kPatchW + (tap % 3);                   // 16-byte granules
+            uint32_t bl = b_lo0 + (uint32_t)(tap * np) * b_step;
+            uint32_t ao = a_off;
+            for (int kk = 0; kk < kpairs; ++kk, bl += 2 * b_step, ao += 2 * (kPlaneStride >> 4)) {
+              const uint64_t bd = ((uint64_t)b_hi32 << 32) | bl;
+#pragma unroll
+              for (int g = 0; g < GN; ++g) umma_bf16(d_tmem + g * NP, a_hi | (uint64_t)(a_lo[g] + ao), bd, idesc, first);
+              first = 1;
             }
-            first = 1;
           }
+        };
+        switch (gn) {
+          case 1: issue(std::integral_constant<int, 1>{}); break;
+          case 2: issue(std::integral_constant<int, 2>{}); break;
+          case 3: issue(std::integral_constant<int, 3>{}); break;
+          default: issue(std::integral_constant<int, 4>{}); break;
         }
-        for (int g = 0; g < gn; ++g) umma_commit(&empty[st_of[g]]);
+        for (int g = 0, st = st_first; g < gn; ++g) {
+          umma_commit(&empty[st]);
+          if (++st == p.stages) st = 0;
+        }
         umma_commit(&tfull[acc]);
       }
     }
+  }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
     // epilogue: warp q reads TMEM lanes [32q, 32q+32); lane m = pixel (m / 8, m % 8) of the 16 x 8 tile
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;       // 0..127
+    const int et = threadIdx.x - 128;      // 0..127
     if (p.stats) {
       for (int i = et; i < 2 * p.Cout; i += 128) s_stats[i] = 0.f;
       asm volatile("bar.sync 1, 128;");
@@ -363,7 +397,7 @@ tc_conv3x3_halo_kernel(HaloParams p) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kProducers) {
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }

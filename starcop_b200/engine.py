@@ -296,10 +296,11 @@ class UNetEngine:
 
     def _halo_ok(self, x, cin, cout, k, stride):
         """thin 3x3 layers (decoder blocks 2-4): one staged halo patch per tile + resident weights (conv_tc_halo.cu)"""
-        # measured on B200 (profiles/r01_layer_bench.txt): it wins where both channel counts are <= 32
-        # (decoder blocks 3.conv2, 4.conv1, 4.conv2: 1.1x ... 3.4x); wider layers stay on the per-tap kernel
+        # measured on B200 (profiles/r02_layer_bench.txt): it wins where one channel count is <= 32 and the other
+        # <= 96 (decoder blocks 3.conv1 80 -> 32 and its dgrad 32 -> 80, 3.conv2, 4.conv1, 4.conv2: 1.2x ... 2.6x);
+        # 64 -> 64 and wider stay on the per-tap kernel (49.8 vs 43.8 us)
         return (self.use_halo and self.dtype == SC_BF16 and self.use_tc and k == 3 and stride == 1 and x.ld % 8 == 0
-                and cin <= 32 and cout <= 32 and bool(_lib.load().sc_tc_halo_supported(cin, cout)))
+                and min(cin, cout) <= 32 and max(cin, cout) <= 96 and bool(_lib.load().sc_tc_halo_supported(cin, cout)))
 
     def _dense_fprop(self, x, wname, k, stride, want_stats=False):
         """-> (y, sums): sums is the fp64 [2*Cout] statistics buffer when the conv epilogue produced it."""
