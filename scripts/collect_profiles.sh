@@ -13,11 +13,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $o/${
 python scripts/launch_summary.py $o/${tag}_launches.csv 100 > $o/${tag}_launch_summary.txt 2>&1
 gzip -f $o/${tag}_launches.csv
 # full captures: the step's heaviest kernel families inside a real step, the largest GEMM, the spectral kernels
-ncu --set full --clock-control none --import-source on -k regex:"tc_conv_wgrad_kernel|bn_bwd_apply|bn_bwd_reduce" --launch-skip 40 -c 10 \
+ncu --set full --clock-control none --import-source on -k regex:"bn_bwd_apply|bn_bwd_reduce|tc_conv3x3_halo|tc_conv_wgrad_kernel" -c 14 \
     -o $o/${tag}_step_kernels python bench.py --steps 1 --warmup 1 --no-cpu-baseline --profile --no-graph --no-spectral > $o/${tag}_ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"tc_conv_fprop" -s 2 -c 1 -o $o/${tag}_conv python scripts/profile_kernels.py dominant > $o/${tag}_ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"mag1c_tc" -s 1 -c 2 -o $o/${tag}_mag1c python scripts/profile_kernels.py mag1c > $o/${tag}_ncu3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"ratio_cluster16|srf" -s 1 -c 1 -o $o/${tag}_ratio python scripts/profile_kernels.py ratio > $o/${tag}_ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"ratio_cluster16" -s 1 -c 1 -o $o/${tag}_ratio python scripts/profile_kernels.py ratio > $o/${tag}_ncu4.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"srf" -s 1 -c 1 -o $o/${tag}_srf python scripts/srf_bench.py > $o/${tag}_ncu5.log 2>&1
 python scripts/layer_bench.py > $o/${tag}_layer_bench.txt 2>&1
 python scripts/dw_bench.py > $o/${tag}_dw_bench.txt 2>&1
