@@ -240,6 +240,17 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partials, int nrow
   __shared__ double sh[2][kRedY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
+  // the owner thread's parameter loads are issued BEFORE the reduction: their latency overlaps the partial-row loads
+  // instead of following the shared-memory combine (this kernel is pure latency, 62 times per step)
+  float pf_g = 1.f, pf_b = 0.f, pf_rm = 0.f, pf_rv = 0.f;
+  if (ty == 0 && c < C) {
+    if (gamma) pf_g = gamma[c];
+    if (beta) pf_b = beta[c];
+    if (running_mean) {
+      pf_rm = running_mean[c];
+      pf_rv = running_var[c];
+    }
+  }
   double s1 = 0.0, s2 = 0.0;
   if (training && c < C) {
     // all of this thread's rows are loaded before the first add: the kernel is one memory latency long, not
@@ -269,21 +280,24 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partials, int nrow
       s1 += sh[0][j][tx];
       s2 += sh[1][j][tx];
     }
-    double m = s1 / (double)P;
-    double var = s2 / (double)P - m * m;   // biased, used for normalisation
+    // reciprocal multiplies instead of three fp64 divisions on the critical path (the owner thread's chain IS the
+    // kernel): 1/P and P/(P-1) are exact-to-rounding constants, rsqrt(double) is accurate to 1 ulp before the cast
+    const double invP = 1.0 / (double)P;
+    double m = s1 * invP;
+    double var = s2 * invP - m * m;        // biased, used for normalisation
     if (var < 0.0) var = 0.0;
     mean = (float)m;
-    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    invstd = (float)rsqrt(var + (double)eps);
     if (running_mean) {
-      double unb = P > 1 ? var * ((double)P / (double)(P - 1)) : var;
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+      double unb = P > 1 ? var * ((double)P * (1.0 / (double)(P - 1))) : var;
+      running_mean[c] = (1.f - momentum) * pf_rm + momentum * mean;
+      running_var[c] = (1.f - momentum) * pf_rv + momentum * (float)unb;
     }
   } else {
-    mean = running_mean[c];
-    invstd = 1.f / sqrtf(running_var[c] + eps);
+    mean = pf_rm;
+    invstd = 1.f / sqrtf(pf_rv + eps);
   }
-  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  float g = pf_g, b = pf_b;
   float sc_ = g * invstd;
   scale[c] = sc_;
   shift[c] = b - mean * sc_;
@@ -760,6 +774,18 @@ __global__ void bn_bwd_totals_kernel(double* __restrict__ partials, int nrows, i
   __shared__ double sh[2][kRedY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
+  // the owner thread's coefficient inputs are fetched before the reduction (latency overlap, see bn_finalize_kernel)
+  float pf_sc = 0.f, pf_sh = 0.f, pf_mu = 0.f, pf_is = 0.f, pf_dg = 0.f, pf_db = 0.f;
+  if (ty == 0 && c < C) {
+    pf_sc = scale[c];
+    pf_sh = shift[c];
+    pf_mu = mean[c];
+    pf_is = invstd[c];
+    if (dgamma) {
+      pf_dg = dgamma[c];
+      pf_db = dbeta[c];
+    }
+  }
   double s1 = 0.0, s2 = 0.0;
   if (c < C) {
     double a[kRedRows], b[kRedRows];
@@ -787,13 +813,13 @@ __global__ void bn_bwd_totals_kernel(double* __restrict__ partials, int nrows, i
   partials[(int64_t)nrows * 2 * C + c] = s1;
   partials[(int64_t)nrows * 2 * C + C + c] = s2;
   if (dgamma) {
-    dbeta[c] += (float)s1;
-    dgamma[c] += (float)s2;
+    dbeta[c] = pf_db + (float)s1;
+    dgamma[c] = pf_dg + (float)s2;
   }
   const float m1 = (float)(s1 * invP), m2 = (float)(s2 * invP);
-  const float sc_ = scale[c], is = invstd[c], mu = mean[c];
+  const float sc_ = pf_sc, is = pf_is, mu = pf_mu;
   coef[c] = sc_;
-  coef[C + c] = shift[c];
+  coef[C + c] = pf_sh;
   coef[2 * C + c] = -sc_ * m2 * is;
   coef[3 * C + c] = sc_ * (m2 * mu * is - m1);
 }
