@@ -54,6 +54,23 @@ inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Division of a non-negative 31-bit integer by a run-time constant as multiply-high + add + shift (Granlund &
+// Montgomery round-up method: q = (mulhi(m, x) + x) >> s with s = ceil(log2 d), m = floor(2^32 (2^s - d) / d) + 1; the
+// sum cannot overflow for x < 2^31).  A hardware-less 32-bit division is ~20 instructions; the persistent tile loops
+// decode (image, tile row, tile column) from the tile index once per tile per thread.
+struct FastDiv {
+  uint32_t m, s, d;
+};
+static inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  f.d = d;
+  f.s = 0;
+  while ((1ull << f.s) < d) ++f.s;
+  f.m = (uint32_t)(((1ull << 32) * ((1ull << f.s) - d)) / d + 1);
+  return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t x, const FastDiv& f) { return (__umulhi(f.m, x) + x) >> f.s; }
+
 // ---- 8-wide channel vectors: the unit every NHWC bandwidth kernel moves (16 B bf16 / 32 B f32)
 struct f8 {
   float v[8];

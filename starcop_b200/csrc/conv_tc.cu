@@ -157,6 +157,7 @@ struct FpropParams {
   int stride;
   int tiles_w, tiles_h;      // spatial patches per image
   int m_tiles, n_tiles;
+  FastDiv div_n, div_w, div_h;   // tile index -> (N tile, image, patch row, patch column) without integer divisions
   int block_n;               // multiple of 16, <= 256
   int cchunks;               // ceil(Cin / KC)
   int groups;                // (tap, channel chunk) K groups per pipeline stage
@@ -220,11 +221,11 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-        int tw = mt % p.tiles_w;
-        int t2 = mt / p.tiles_w;
-        int th = t2 % p.tiles_h;
-        int img = t2 / p.tiles_h;
+        int mt = (int)fast_div((uint32_t)tile, p.div_n), nt = tile - mt * p.n_tiles;
+        int t2 = (int)fast_div((uint32_t)mt, p.div_w);
+        int tw = mt - t2 * p.tiles_w;
+        int img = (int)fast_div((uint32_t)t2, p.div_h);
+        int th = t2 - img * p.tiles_h;
         int n0 = nt * p.block_n;
         const int w0 = (tw * 16) * p.stride - pad, h0 = (th * 8) * p.stride - pad;
         const int group_tx = A_BYTES + p.block_n * ROW_BYTES;
@@ -312,11 +313,11 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      int mt = tile / p.n_tiles, nt = tile - mt * p.n_tiles;
-      int tw = mt % p.tiles_w;
-      int t2 = mt / p.tiles_w;
-      int th = t2 % p.tiles_h;
-      int img = t2 / p.tiles_h;
+      int mt = (int)fast_div((uint32_t)tile, p.div_n), nt = tile - mt * p.n_tiles;
+      int t2 = (int)fast_div((uint32_t)mt, p.div_w);
+      int tw = mt - t2 * p.tiles_w;
+      int img = (int)fast_div((uint32_t)t2, p.div_h);
+      int th = t2 - img * p.tiles_h;
       int n0 = nt * p.block_n;
       mbar_wait(&tfull[acc], (it >> 1) & 1);
       tc_fence_after();
@@ -499,6 +500,9 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
   int nt = (Cout + 255) / 256;
   p.block_n = ((Cout + nt - 1) / nt + 15) / 16 * 16;
   p.n_tiles = (Cout + p.block_n - 1) / p.block_n;
+  p.div_n = make_fastdiv((uint32_t)p.n_tiles);
+  p.div_w = make_fastdiv((uint32_t)p.tiles_w);
+  p.div_h = make_fastdiv((uint32_t)p.tiles_h);
   p.cchunks = (Cin + kc - 1) / kc;      // a ragged last chunk is zero-filled by TMA (and by the weight pack)
   p.ldy = ldy; p.y = (__nv_bfloat16*)y; p.stats = stats; p.accumulate = accumulate;
   const int ksteps = KH * KW * p.cchunks;

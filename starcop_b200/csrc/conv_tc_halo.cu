@@ -48,6 +48,7 @@ struct HaloParams {
   int N, H, W, Cin, Cout;
   int np;                      // channel planes per patch = cin_pad16 / 8
   int tiles_w, tiles_h, m_tiles;
+  FastDiv div_w, div_h;        // tile index -> (image, tile row, tile column) without integer divisions
   int stages, ldy, accumulate;
   int batch, ncols;            // tiles per MMA batch, TMEM columns per accumulator
   int tmem_cols;               // allocation: power of two >= 2 * batch * ncols
@@ -141,10 +142,10 @@ tc_conv3x3_halo_kernel(HaloParams p) {
     uint32_t phase = 0;
     const uint32_t sA_u32 = smem_u32(sA);
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      const int tw = tile % p.tiles_w;
-      const int t2 = tile / p.tiles_w;
-      const int th = t2 % p.tiles_h;
-      const int img = t2 / p.tiles_h;
+      const int t2 = (int)fast_div((uint32_t)tile, p.div_w);
+      const int tw = tile - t2 * p.tiles_w;
+      const int img = (int)fast_div((uint32_t)t2, p.div_h);
+      const int th = t2 - img * p.tiles_h;
       const int h0 = th * kTileH - 1, w0 = tw * kTileW - 1;
       mbar_wait(&empty[stage], phase ^ 1);
       const __nv_bfloat16* base = p.x + (((int64_t)img * p.H + h0) * p.W + w0) * p.ldx;
@@ -275,10 +276,10 @@ tc_conv3x3_halo_kernel(HaloParams p) {
         yp[g] = p.y;
         if (g < gn) {
           const int tile = blockIdx.x + (t0 + g) * gridDim.x;
-          const int tw = tile % p.tiles_w;
-          const int t2 = tile / p.tiles_w;
-          const int th = t2 % p.tiles_h;
-          const int img = t2 / p.tiles_h;
+          const int t2 = (int)fast_div((uint32_t)tile, p.div_w);
+          const int tw = tile - t2 * p.tiles_w;
+          const int img = (int)fast_div((uint32_t)t2, p.div_h);
+          const int th = t2 - img * p.tiles_h;
           const int h = th * kTileH + (row >> 3), w = tw * kTileW + (row & 7);
           valid[g] = h < p.H && w < p.W;
           yp[g] = p.y + (((int64_t)img * p.H + h) * p.W + w) * p.ldy;
@@ -432,6 +433,8 @@ extern "C" int sc_tc_conv3x3_halo(const void* x, int ldx, const void* w_bf16, vo
   p.np = sc_tc_halo_cin_pad(Cin) / 8;
   p.tiles_w = (W + kTileW - 1) / kTileW;
   p.tiles_h = (H + kTileH - 1) / kTileH;
+  p.div_w = make_fastdiv((uint32_t)p.tiles_w);
+  p.div_h = make_fastdiv((uint32_t)p.tiles_h);
   const int64_t mt = (int64_t)N * p.tiles_w * p.tiles_h;
   if (mt > INT32_MAX) return SC_ERR_BAD_ARG;
   p.m_tiles = (int)mt;
