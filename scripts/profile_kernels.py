@@ -20,7 +20,8 @@ if what in ("all", "dominant"):
     m = get_model(default_settings(compute_dtype="bf16"), None).cuda()
     print(m.network.bench_dominant_kernel(B, S, iters=3))
 if what in ("all", "halo"):
-    cin = cout = 16
+    cin, cout = int(os.environ.get("HALO_CIN", 16)), int(os.environ.get("HALO_COUT", 16))
+    S = int(os.environ.get("HALO_S", S))
     x = torch.randn(B, S, S, cin, device="cuda").bfloat16(); y = torch.empty(B, S, S, cout, device="cuda", dtype=torch.bfloat16)
     w = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
     hp = lib.sc_tc_halo_cin_pad(cin)

@@ -210,6 +210,26 @@ def test_head(dtype):
     assert torch.allclose(nchw(dx), gx, **tol(dtype))
 
 
+@pytest.mark.parametrize("h,w", [(8, 32), (40, 24), (19, 37), (64, 96), (7, 5)])
+def test_head_tiled_kernels_ragged_sizes(h, w):
+    """the shared-memory tiled head kernels (16 bf16 channels): tiles of 8 x 32 outputs with ragged borders, several
+    tiles per CTA (the cp.async ring wraps), against torch's Conv2d on the same bf16 inputs"""
+    torch.manual_seed(11)
+    N, C = 3, 16
+    x = nhwc(torch.randn(N, C, h, w, device=DEV), SC_BF16)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    conv = torch.nn.Conv2d(C, 1, 3, padding=1).to(DEV)
+    yr = conv(xr)
+    lg = torch.full((N, 1, h, w), float("nan"), device=DEV)
+    call("sc_head_fprop", x.data_ptr(), C, conv.weight.data_ptr(), conv.bias.data_ptr(), lg.data_ptr(), N, h, w, C, SC_BF16, st())
+    assert torch.allclose(lg, yr, rtol=1e-5, atol=1e-5)
+    dl = torch.randn_like(yr)
+    gx, = torch.autograd.grad(yr, [xr], dl)
+    dx = torch.full((N, h, w, C), float("nan"), device=DEV, dtype=TDT[SC_BF16])
+    call("sc_head_bwd", x.data_ptr(), C, conv.weight.data_ptr(), dl.data_ptr(), dx.data_ptr(), C, N, h, w, C, SC_BF16, st())
+    assert torch.allclose(nchw(dx), gx, **tol(SC_BF16))
+
+
 @pytest.mark.parametrize("dtype", [SC_F32, SC_BF16])
 @pytest.mark.parametrize("C,h,w", [(16, 32, 32), (16, 40, 24), (8, 19, 37), (64, 16, 16), (32, 64, 48)])
 def test_head_wgrad_tiled(dtype, C, h, w):

@@ -88,7 +88,9 @@ def test_tc_dgrad_via_flipped_weights(Cin, Cout):
     assert torch.allclose(dx.float(), 2 * gx.permute(0, 2, 3, 1), rtol=3e-2, atol=4e-2)
 
 
-@pytest.mark.parametrize("N,H,W,Cin,Cout,k", CASES + [(16, 64, 64, 32, 16, 3), (4, 32, 32, 16, 16, 3)])
+# the last three: many pixel splits per gradient block -> the grouped split reduction with its last-arrival tail
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k", CASES + [(16, 64, 64, 32, 16, 3), (4, 32, 32, 16, 16, 3), (8, 128, 128, 24, 144, 1),
+                                                 (4, 128, 128, 64, 64, 3), (4, 256, 256, 16, 96, 1)])
 def test_tc_wgrad(N, H, W, Cin, Cout, k):
     x, w = make(N, H, W, Cin, Cout, k, seed=1)
     dy = torch.randn(N, H, W, Cout, device=DEV).to(torch.bfloat16)
