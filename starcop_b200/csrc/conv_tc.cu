@@ -165,11 +165,16 @@ struct FpropParams {
   int ldy;
   int accumulate;            // y += result (gradient fan-in)
   int tmem_cols;             // 2 accumulator stages: 512, or 256 when two CTAs share an SM
+  int b_resident;            // > 0: byte offset (from the barrier block) of the CTA-resident weights [n tile][K step]
   __nv_bfloat16* y;
   double* stats;             // optional [2][Cout] fp64 sum / sum of squares of the stored outputs
 };
 
 constexpr int kTcThreads = 192;
+#ifndef SC_EPI_BATCH
+#define SC_EPI_BATCH 4
+#endif
+constexpr int kEpiBatch = SC_EPI_BATCH;   // TMEM loads in flight behind one wait in the store-bound epilogue
 constexpr int kMaxDynSmem = 227 * 1024;
 
 template <int KC>
@@ -182,12 +187,13 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   constexpr int A_BYTES = 128 * ROW_BYTES;
   const int B_BYTES = (p.block_n * ROW_BYTES + 1023) & ~1023;
   const int G = p.groups;
-  const int STAGE_BYTES = G * (A_BYTES + B_BYTES);       // [G x A][G x B], every box 1024-aligned
+  const int STAGE_BYTES = G * (A_BYTES + (p.b_resident ? 0 : B_BYTES));       // [G x A][G x B], every box 1024-aligned
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * STAGE_BYTES);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bres = tempty + 2;                                  // the resident weight tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres + 1);
   float* s_stats = reinterpret_cast<float*>(tmem_slot + 4);     // [2][Cout] per-CTA partial statistics
   float* s_part = s_stats + 2 * p.Cout;                         // [4 warps][2][block_n] one tile's column sums
 
@@ -201,6 +207,7 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 128);
     }
+    mbar_init(bres, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -220,6 +227,17 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      // Layers whose whole packed weight matrix fits beside the pipeline: fetched ONCE per CTA.  TMA retires a box row
+      // every few cycles whatever its width, and with 16-32 input channels the Cout weight rows of a tile cost as much
+      // as its 128 activation rows (f2.exp fprop, no epilogue work at all: 49 us for 33 MB of input; 89 -> 52 us with
+      // the stores once the weights were resident)
+      uint8_t* sBres = reinterpret_cast<uint8_t*>(full) + p.b_resident;
+      if (p.b_resident) {
+        mbar_arrive_expect_tx(bres, (uint32_t)(p.n_tiles * ksteps * p.block_n * ROW_BYTES));
+        for (int nt = 0; nt < p.n_tiles; ++nt)
+          for (int ks = 0; ks < ksteps; ++ks)
+            tma_load_2d(sBres + (size_t)(nt * ksteps + ks) * B_BYTES, &tmB, ks * KC, nt * p.block_n, bres);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int mt = (int)fast_div((uint32_t)tile, p.div_n), nt = tile - mt * p.n_tiles;
         int t2 = (int)fast_div((uint32_t)mt, p.div_w);
@@ -228,7 +246,7 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         int th = t2 - img * p.tiles_h;
         int n0 = nt * p.block_n;
         const int w0 = (tw * 16) * p.stride - pad, h0 = (th * 8) * p.stride - pad;
-        const int group_tx = A_BYTES + p.block_n * ROW_BYTES;
+        const int group_tx = A_BYTES + (p.b_resident ? 0 : p.block_n * ROW_BYTES);
         int cc = 0, kw = 0, kh = 0;             // running (channel chunk, tap) of the next K group: no divisions
         for (int s0 = 0; s0 < ksteps; s0 += G) {
           const int g_here = min(G, ksteps - s0);
@@ -238,7 +256,7 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_arrive_expect_tx(&full[stage], g_here * group_tx);
           for (int g = 0; g < g_here; ++g) {
             tma_load_4d(sA + g * A_BYTES, &tmA, cc * KC, w0 + kw, h0 + kh, img, &full[stage]);
-            tma_load_2d(sB + g * B_BYTES, &tmB, (s0 + g) * KC, n0, &full[stage]);
+            if (!p.b_resident) tma_load_2d(sB + g * B_BYTES, &tmB, (s0 + g) * KC, n0, &full[stage]);
             if (++cc == p.cchunks) {
               cc = 0;
               if (++kw == p.KW) {
@@ -265,11 +283,18 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
+      const uint32_t bres_lo = desc_lo0 + (uint32_t)((p.stages * STAGE_BYTES + p.b_resident) >> 4);
+      if (p.b_resident) {
+        mbar_wait(bres, 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(&tempty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (p.tmem_cols / 2);
+        const int nt_mma = tile - (int)fast_div((uint32_t)tile, p.div_n) * p.n_tiles;
+        const uint32_t bres_tile = bres_lo + (uint32_t)(nt_mma * ksteps) * (uint32_t)(B_BYTES >> 4);
         for (int si = 0; si < nstages_per_tile; ++si) {
           const int g_here = min(G, ksteps - si * G);
           mbar_wait(&full[stage], phase);
@@ -278,7 +303,8 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           // address in 16-byte units; shared memory < 256 KB, the 14-bit field never carries) -- the issuing thread
           // is the limit on the thin layers, every instruction between two MMAs counts
           const uint32_t a_lo = desc_lo0 + (uint32_t)stage * (uint32_t)(STAGE_BYTES >> 4);
-          const uint32_t b_lo = a_lo + (uint32_t)(G * A_BYTES >> 4);
+          const uint32_t b_lo = p.b_resident ? bres_tile + (uint32_t)(si * G) * (uint32_t)(B_BYTES >> 4)
+                                             : a_lo + (uint32_t)(G * A_BYTES >> 4);
           for (int g = 0; g < g_here; ++g) {
 #pragma unroll
             for (int k = 0; k < KC / 16; ++k) {
@@ -330,15 +356,15 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // flight behind ONE tcgen05.wait::ld, then the 256-bit stores back to back -- the per-chunk load -> wait ->
         // store chain cost one TMEM round trip per 16 channels (f2.exp fprop 112 us for 235 MB)
         const int full = min(p.block_n, (p.Cout - n0) & ~15);       // columns covered by complete 16-channel groups
-        for (; c_begin + 16 <= full; c_begin += 64) {
-          uint32_t r[4][16];
-          const int ng = min(4, (full - c_begin) / 16);
+        for (; c_begin + 16 <= full; c_begin += 16 * kEpiBatch) {
+          uint32_t r[kEpiBatch][16];
+          const int ng = min(kEpiBatch, (full - c_begin) / 16);
 #pragma unroll
-          for (int g = 0; g < 4; ++g)
+          for (int g = 0; g < kEpiBatch; ++g)
             if (g < ng) tmem_ld16_nowait(taddr + c_begin + 16 * g, r[g]);
           tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
+          for (int g = 0; g < kEpiBatch; ++g) {
             if (g < ng) {
               uint32_t w8[8];
 #pragma unroll
@@ -516,8 +542,16 @@ extern "C" int sc_tc_conv_fprop(const void* x, int ldx, const void* w_bf16, void
   while (groups > 1 && groups * group_bytes > 64 * 1024) --groups;
   if (groups < 1) groups = 1;
   p.groups = groups;
-  const int stage_bytes = groups * group_bytes;
-  const int tail = 1024 + 256 + (stats ? (2 * Cout + 8 * p.block_n) * 4 : 0);   // alignment slack + barriers + statistics
+  const int b_tile_bytes = (p.block_n * kc * 2 + 1023) & ~1023;
+  // resident weights (kernel comment): all (N tile, K step) weight tiles, when they are small next to the pipeline
+  static const int kBresMax = getenv("STARCOP_BRES_KB") ? atoi(getenv("STARCOP_BRES_KB")) * 1024 : 48 * 1024;
+  const int b_all_bytes = p.n_tiles * ksteps * b_tile_bytes;
+  const bool bres = b_all_bytes <= kBresMax && !getenv("STARCOP_NO_BRES");
+  // 1024-aligned (swizzle atoms), behind the barrier / statistics block
+  const int stats_bytes = stats ? (2 * Cout + 8 * p.block_n) * 4 : 0;
+  p.b_resident = bres ? (256 + stats_bytes + 1023) & ~1023 : 0;
+  const int tail = 1024 + (bres ? p.b_resident + b_all_bytes : 256 + stats_bytes);   // alignment slack + barriers + statistics (+ weights)
+  const int stage_bytes = groups * (bres ? 128 * kc * 2 : group_bytes);               // resident weights: the stages hold activations only
   // Short-K layers (the 1x1 expansions / projections: one or two MMAs per tile) are bound by the per-tile
   // TMA -> MMA -> epilogue hand-offs, not by the tensor pipe: run TWO CTAs per SM (half the shared memory,
   // 256 TMEM columns each) so twice as many tiles are in flight.
