@@ -498,7 +498,13 @@ tc_conv_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 // channel chunk = swizzle span of one TMA box: the widest of 64 / 32 / 16 whose zero padding of the
 // ragged last chunk stays small (padding costs MMA cycles only: TMA zero-fills out-of-range channels)
 static int pick_kc(int C) {
+  // channel chunk = TMA box row = one swizzle row (32 / 64 / 128 bytes).  TMA retires a box row every few cycles
+  // whatever its width, and the thin layers are bound by exactly that row rate (per-tap wgrad of 152 -> 64: 46 rows
+  // per pixel at 32-channel chunks = 187 us of row issue for a 208 us kernel), so above 32 channels the widest row
+  // wins even when it pads K (the tensor pipe idles on these layers anyway).  STARCOP_KC_RULE=old: <= 12.5 % padding.
+  static const bool old_rule = getenv("STARCOP_KC_RULE") && getenv("STARCOP_KC_RULE")[0] == 'o';
   if (C <= 16) return 16;
+  if (!old_rule) return C <= 32 ? 32 : 64;
   int p64 = (C + 63) / 64 * 64;
   if ((p64 - C) * 8 <= C) return 64;      // <= 12.5 % padding
   return 32;
