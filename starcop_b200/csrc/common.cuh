@@ -35,6 +35,10 @@ __device__ __forceinline__ void pdl_wait() {
 #endif
 }
 
+// for tiny single-wave kernels only: lets the successor's CTAs be dispatched while this kernel runs (they block in
+// their own pdl_wait until this grid has completed).  Measured harmful as a blanket policy, see DESIGN.md.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 bool pdl_enabled();   // elementwise.cu: reads STARCOP_PDL once
 
 template <typename... KArgs, typename... Args>

@@ -292,6 +292,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partials, int nrow
                                    int training, float* scale, float* shift, float* save_mean,
                                    float* save_invstd) {
   sc::pdl_wait();
+#ifdef SC_PDL_TRIGGER_TINY
+  sc::pdl_trigger();
+#endif
   __shared__ double sh[2][kRedY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
@@ -826,6 +829,9 @@ __global__ void bn_bwd_totals_kernel(double* __restrict__ partials, int nrows, i
                                      const float* __restrict__ mean, const float* __restrict__ invstd,
                                      float* dgamma, float* dbeta, float* __restrict__ coef) {
   sc::pdl_wait();
+#ifdef SC_PDL_TRIGGER_TINY
+  sc::pdl_trigger();
+#endif
   __shared__ double sh[2][kRedY][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
