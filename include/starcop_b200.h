@@ -297,6 +297,14 @@ int sc_tc_wgrad_halo(const void* x, int ldx, const void* dy, int lddy, float* dw
  * taps' weights stay resident in shared memory.  Packed weights: bf16 [Cout][9][sc_tc_halo_cin_pad(Cin)]
  * (sc_tc_pack_weights with cin_pad = that value).  Any H, W; Cin % 8 == 0; Cout % 16 == 0, Cout <= 128. */
 int sc_tc_halo_cin_pad(int Cin);
+/* Stem Conv2d(C <= 4 -> Cout, 3x3, stride 2, pad 1) -- the first layer of torchvision MobileNetV2 inside
+ * smp.Unet(mobilenet_v2), starcop/models/model_module.py:238-251 -- as a space-to-depth convolution:
+ * sc_stem_s2d regroups the bf16 NHWC input (N,H,W,ld) into (N,H/2,W/2,16), sc_stem_s2d_pack_weights writes the
+ * equivalent stride-1 3x3 weights over 16 channels in the tensor-core packing [Cout][9][16], sc_stem_s2d_unpack_grad
+ * adds the gradient of those weights (Cout,16,3,3 fp32) back into the OIHW gradient (Cout,C,3,3). */
+int sc_stem_s2d(const void* x_nhwc, int ldx, int C, void* xs, int N, int H, int W, void* stream);
+int sc_stem_s2d_pack_weights(const float* w_oihw, void* w_bf16, int Cout, int C, void* stream);
+int sc_stem_s2d_unpack_grad(const float* g_s2d, float* dw_oihw, int Cout, int C, void* stream);
 int sc_tc_halo_supported(int Cin, int Cout);
 int sc_tc_conv3x3_halo(const void* x, int ldx, const void* w_bf16, void* y, int ldy, double* stats,
                        int* stats_rows_host, int N, int H, int W, int Cin, int Cout, int accumulate, void* stream);

@@ -64,6 +64,9 @@ SIGNATURES = {
     "sc_tc_cin_pad": [I],
     "sc_tc_conv_fprop": [P, I, P, P, I, P, P, I, I, I, I, I, I, I, I, I, P],
     "sc_tc_halo_cin_pad": [I],
+    "sc_stem_s2d": [P, I, I, P, I, I, I, P],
+    "sc_stem_s2d_pack_weights": [P, P, I, I, P],
+    "sc_stem_s2d_unpack_grad": [P, P, I, I, P],
     "sc_tc_halo_supported": [I, I],
     "sc_tc_conv3x3_halo": [P, I, P, P, I, P, P, I, I, I, I, I, I, P],
     "sc_tc_conv_wgrad_workspace_bytes": [I, I, I, I, I, I, I, I],

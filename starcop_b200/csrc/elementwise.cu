@@ -939,6 +939,86 @@ extern "C" int sc_add_into(const void* a, int lda, int pooled, void* out, int ld
 }
 
 // ------------------------------------------------------------------------------------------------
+// Stem as a space-to-depth convolution.  The network's first layer is Conv2d(C <= 4 -> 32, 3x3, stride 2): on the
+// tensor cores that is nine stride-2 TMA boxes of 16-byte pixels per tile (fprop 94 us for 134 MB) and -- worse -- a
+// weight gradient whose 166 us are the LAST thing the backward pass does, fully exposed before Adam.  With the input
+// regrouped as (N, H/2, W/2, 16) -- channel (sy*2 + sx)*4 + c = input pixel (2Y + sy, 2X + sx), channel c -- the same
+// convolution is a stride-1 3x3 convolution over 16 channels whose taps ty, tx in {0, 1} carry the original taps
+//      ky -> (ty, sy):  0 -> (0, 1),  1 -> (1, 0),  2 -> (1, 1)      (same for kx), every other weight zero,
+// i.e. a layer the halo kernels (one staged patch per tile, fprop and wgrad) already run at full speed.  Zero weights
+// contribute exactly zero, so the result differs from the direct form only by summation order.
+// ------------------------------------------------------------------------------------------------
+__global__ void stem_s2d_kernel(const __nv_bfloat16* __restrict__ x, int ldx, int C, __nv_bfloat16* __restrict__ xs, int H, int W,
+                                int64_t total) {
+  sc::pdl_wait();
+  const int H2 = H / 2, W2 = W / 2;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int X = (int)(i % W2);
+    const int64_t t = i / W2;
+    const int Y = (int)(t % H2);
+    const int64_t n = t / H2;
+    __align__(16) __nv_bfloat16 o[16];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const __nv_bfloat16* src = x + ((n * H + 2 * Y + (q >> 1)) * W + 2 * X + (q & 1)) * ldx;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[q * 4 + c] = c < C ? src[c] : __float2bfloat16_rn(0.f);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(xs + i * 16);
+    dst[0] = reinterpret_cast<const uint4*>(o)[0];
+    dst[1] = reinterpret_cast<const uint4*>(o)[1];
+  }
+}
+__device__ __forceinline__ bool stem_s2d_map(int ch, int ty, int tx, int C, int& c, int& ky, int& kx) {
+  const int q = ch >> 2, sy = q >> 1, sx = q & 1;
+  c = ch & 3;
+  // (t, s) -> k:  (0,1) -> 0, (1,0) -> 1, (1,1) -> 2; (0,0) and t = 2 carry nothing
+  ky = ty == 0 ? (sy == 1 ? 0 : -1) : (ty == 1 ? 1 + sy : -1);
+  kx = tx == 0 ? (sx == 1 ? 0 : -1) : (tx == 1 ? 1 + sx : -1);
+  return c < C && ky >= 0 && kx >= 0;
+}
+// w (Cout, C, 3, 3) fp32 -> bf16 [Cout][9 taps][16 channels] (the tensor-core packing of the equivalent weights)
+__global__ void stem_s2d_pack_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wb, int Cout, int C) {
+  sc::pdl_wait();
+  const int total = Cout * 9 * 16;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ch = i & 15, tap = (i >> 4) % 9, co = i / 144;
+    int c, ky, kx;
+    const bool ok = stem_s2d_map(ch, tap / 3, tap % 3, C, c, ky, kx);
+    wb[i] = __float2bfloat16_rn(ok ? w[((co * C + c) * 3 + ky) * 3 + kx] : 0.f);
+  }
+}
+// dW (Cout, C, 3, 3) += the non-zero positions of the equivalent weights' gradient g (Cout, 16, 3, 3)
+__global__ void stem_s2d_unpack_grad_kernel(const float* __restrict__ g, float* __restrict__ dw, int Cout, int C) {
+  sc::pdl_wait();
+  const int total = Cout * 16 * 9;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 9, ch = (i / 9) & 15, co = i / 144;
+    int c, ky, kx;
+    if (stem_s2d_map(ch, tap / 3, tap % 3, C, c, ky, kx)) dw[((co * C + c) * 3 + ky) * 3 + kx] += g[i];
+  }
+}
+
+extern "C" int sc_stem_s2d(const void* x_nhwc, int ldx, int C, void* xs, int N, int H, int W, void* stream) {
+  if (!x_nhwc || !xs || C < 1 || C > 4 || ldx < C || (H & 1) || (W & 1) || N <= 0 || (reinterpret_cast<uintptr_t>(xs) & 15))
+    return SC_ERR_BAD_ARG;
+  const int64_t total = (int64_t)N * (H / 2) * (W / 2);
+  sc::launch_pdl((stem_s2d_kernel), ew_blocks(total), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x_nhwc, ldx, C,
+                 (__nv_bfloat16*)xs, H, W, total);
+  return check_launch();
+}
+extern "C" int sc_stem_s2d_pack_weights(const float* w_oihw, void* w_bf16, int Cout, int C, void* stream) {
+  if (!w_oihw || !w_bf16 || Cout < 1 || C < 1 || C > 4) return SC_ERR_BAD_ARG;
+  sc::launch_pdl((stem_s2d_pack_kernel), (Cout * 144 + 255) / 256, 256, 0, (cudaStream_t)stream, w_oihw, (__nv_bfloat16*)w_bf16, Cout, C);
+  return check_launch();
+}
+extern "C" int sc_stem_s2d_unpack_grad(const float* g_s2d, float* dw_oihw, int Cout, int C, void* stream) {
+  if (!g_s2d || !dw_oihw || Cout < 1 || C < 1 || C > 4) return SC_ERR_BAD_ARG;
+  sc::launch_pdl((stem_s2d_unpack_grad_kernel), (Cout * 144 + 255) / 256, 256, 0, (cudaStream_t)stream, g_s2d, dw_oihw, Cout, C);
+  return check_launch();
+}
+
+// ------------------------------------------------------------------------------------------------
 // segmentation head: Conv2d(C->1, 3x3, pad 1, bias).  AI 8.5 FLOP/B -> one thread per pixel.
 // ------------------------------------------------------------------------------------------------
 constexpr int kHeadMaxC = 64;

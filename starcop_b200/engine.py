@@ -323,7 +323,7 @@ class UNetEngine:
             wb = self._packed(wname, k, 0, cpad, cout)
             # the statistics epilogue costs ~(Cout/16) x 300 cycles per 128-pixel tile: worth fusing only
             # when the tile's K loop is long enough to hide it, else the separate pass over y is cheaper
-            want_stats = want_stats and cin * k * k >= 256
+            want_stats = want_stats and cin * k * k >= int(os.environ.get("STARCOP_STATS_MIN_K", 256))
             part, n = (self._partials(cout), ctypes.c_int(0)) if want_stats else (0, ctypes.c_int(0))
             tn, th, tw = self._tc_dims(x, k, stride)
             call("sc_tc_conv_fprop", x.ptr, x.ld, wb, y.ptr, y.ld, part, ctypes.byref(n), tn, th, tw, cin, cout,
@@ -383,6 +383,46 @@ class UNetEngine:
             def bwd():
                 dy = self._bn_backward(z, y, bn, stats, act, up2)
                 self._dense_backward(x, dy, wname, k, stride, need_dx)
+            self.tape.append(bwd)
+        return z
+
+    def _stem_s2d_ok(self, x, cout):
+        return (self.use_tc and self.use_halo and self.dtype == SC_BF16 and x.C <= 4 and x.H % 2 == 0 and x.W % 2 == 0
+                and os.environ.get("STARCOP_NO_STEM_S2D", "") == "" and bool(_lib.load().sc_tc_halo_supported(16, cout))
+                and bool(_lib.load().sc_tc_wgrad_halo_supported(x.N, x.H // 2, x.W // 2, 16, cout)))
+
+    def stem_conv_bn_act(self, x, wname, bn, act, training):
+        """The stride-2 stem as a space-to-depth convolution (csrc/elementwise.cu, sc_stem_s2d): a stride-1 3x3 layer
+        over 16 channels on the halo kernels.  Its weight gradient is the last kernel of the backward pass and sits
+        fully exposed before Adam: 166 us on the per-tap kernel (nine stride-2 boxes of 16-byte pixels per stage)."""
+        w = self.p[wname]
+        cout = w.shape[0]
+        if not self._stem_s2d_ok(x, cout):
+            return self.conv_bn_act(x, wname, bn, 3, 2, act, training, need_dx=False)
+        N, H2, W2 = x.N, x.H // 2, x.W // 2
+        xs = self.new(N, H2, W2, 16)
+        call("sc_stem_s2d", x.ptr, x.ld, x.C, xs.ptr, N, x.H, x.W, self.stream)
+        if getattr(self, "_stem_wb", None) is None or self._stem_wb.numel() != cout * 144:
+            self._stem_wb = torch.empty(cout * 144, dtype=torch.bfloat16, device=self.device)
+        call("sc_stem_s2d_pack_weights", w.data_ptr(), self._stem_wb.data_ptr(), cout, x.C, self.stream)
+        y = self.new(N, H2, W2, cout)
+        part, n = (self._partials(cout), ctypes.c_int(0)) if training else (0, ctypes.c_int(0))
+        call("sc_tc_conv3x3_halo", xs.ptr, 16, self._stem_wb.data_ptr(), y.ptr, y.ld, part, ctypes.byref(n), N, H2, W2, 16, cout,
+             0, self.stream)
+        stats = self._bn_forward(y, bn, training, (part, n.value) if training else None)
+        z = self._bn_act(y, stats[0], stats[1], act)
+        if self.record:
+            C = x.C
+
+            def bwd():
+                dy = self._bn_backward(z, y, bn, stats, act, False)
+                lib = _lib.load()
+                g16 = self.f32buf(cout * 144, zero=True)
+                nb = lib.sc_tc_conv_wgrad_workspace_bytes(N, H2, W2, 16, cout, 3, 3, 1)
+                ws = self.arena.alloc(nb) if nb > 0 else 0
+                st = self._wgrad_stream()
+                call("sc_tc_conv_wgrad", xs.ptr, 16, dy.ptr, dy.ld, g16, ws, N, H2, W2, 16, cout, 3, 3, 1, st)
+                call("sc_stem_s2d_unpack_grad", g16, self.g[wname].data_ptr(), cout, C, st)
             self.tape.append(bwd)
         return z
 
@@ -475,7 +515,7 @@ class UNetEngine:
 
         skip_obj, up_src = {}, {}
         # ---- encoder
-        x = self.conv_bn_act(x_nhwc, f"{E}.0.0.weight", f"{E}.0.1", 3, 2, ACT_RELU6, training, need_dx=False)
+        x = self.stem_conv_bn_act(x_nhwc, f"{E}.0.0.weight", f"{E}.0.1", ACT_RELU6, training)
         idx, cin = 1, 32
         for t, c, n, s in MBV2_SETTING:
             for r in range(n):

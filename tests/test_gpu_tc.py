@@ -134,6 +134,40 @@ def test_tc_stem_stride2_fprop_and_wgrad():
     assert (dw - gw).abs().max().item() <= 2e-3 * gw.abs().max().item()
 
 
+@pytest.mark.parametrize("N,H,W,Cin", [(2, 32, 64, 4), (1, 64, 32, 3), (2, 64, 96, 1)])
+def test_stem_space_to_depth_equals_the_stride2_convolution(N, H, W, Cin):
+    """the stem as a space-to-depth convolution (sc_stem_s2d + equivalent 3x3 weights over 16 channels on the halo
+    kernels): same outputs and the same weight gradient as Conv2d(Cin, 32, 3, stride 2, pad 1)"""
+    Cout = 32
+    torch.manual_seed(5)
+    x8 = torch.zeros(N, H, W, 8, device=DEV, dtype=torch.bfloat16)
+    x8[..., :Cin] = torch.randn(N, H, W, Cin, device=DEV).to(torch.bfloat16)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV) / 6
+    H2, W2 = H // 2, W // 2
+    xs = torch.full((N, H2, W2, 16), float("nan"), device=DEV, dtype=torch.bfloat16)
+    call("sc_stem_s2d", x8.data_ptr(), 8, Cin, xs.data_ptr(), N, H, W, st())
+    wb = torch.empty(Cout * 144, device=DEV, dtype=torch.bfloat16)
+    call("sc_stem_s2d_pack_weights", w.data_ptr(), wb.data_ptr(), Cout, Cin, st())
+    y = torch.full((N, H2, W2, Cout), float("nan"), device=DEV, dtype=torch.bfloat16)
+    import ctypes
+    n = ctypes.c_int(0)
+    call("sc_tc_conv3x3_halo", xs.data_ptr(), 16, wb.data_ptr(), y.data_ptr(), Cout, 0, ctypes.byref(n), N, H2, W2, 16, Cout, 0, st())
+    xr = x8[..., :Cin].float().permute(0, 3, 1, 2)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, stride=2, padding=1)
+    assert torch.allclose(y.float(), ref.permute(0, 2, 3, 1), rtol=2e-2, atol=2e-2)
+    dy = torch.randn(N, H2, W2, Cout, device=DEV).to(torch.bfloat16)
+    g16 = torch.zeros(Cout, 16, 3, 3, device=DEV)
+    ops.tc_conv_wgrad(xs, 16, dy, Cout, g16, N, H2, W2, 16, Cout, 3)
+    dw = torch.zeros(Cout, Cin, 3, 3, device=DEV)
+    call("sc_stem_s2d_unpack_grad", g16.data_ptr(), dw.data_ptr(), Cout, Cin, st())
+    (gw,) = torch.autograd.grad(ref, wr, dy.float().permute(0, 3, 1, 2))
+    assert (dw - gw).abs().max().item() <= 2e-3 * gw.abs().max().item()
+    # the positions of the equivalent weights that carry no original tap have zero weight (their gradient is ignored)
+    wd = wb.float().view(Cout, 9, 16)
+    assert int((wd != 0).sum()) <= Cout * 9 * Cin
+
+
 HALO_CASES = [  # N, H, W, Cin, Cout
     (1, 16, 8, 16, 16),       # one tile, one K pair
     (2, 32, 32, 32, 16),      # decoder block 4 conv1 geometry, several tiles
