@@ -188,6 +188,8 @@ int sc_mag1c_filter(const void* x, int64_t pixel_stride, const int32_t* pix_idx,
 /* diagnostics: clock64 stamps of group 0 at the phase boundaries of the last tensor-core mag1c launch
  * (start, loaded, centred, MMAs done, covariance assembled, inverse done, rmf end, iteration 0 end, end) */
 int sc_debug_mag1c_clocks(long long* out16);
+/* x / d for 0 <= x < 2^31, d >= 1, evaluated with the multiply-high constants the persistent tile loops use (host only; tests) */
+unsigned int sc_debug_fastdiv(unsigned int x, unsigned int d);
 
 /* ---- A11/A13: band ratio product (starcop/data/feature_extration.py:32-56) ------------------
  * per tile: exact 5/95 percentiles (np.percentile linear) of each band by radix select, inlier

@@ -46,6 +46,7 @@ SIGNATURES = {
     "sc_mag1c_smem_bytes": [I, I, I],
     "sc_mag1c_filter": [P, L, P, P, I, P, P, P, I, I, I, D, I, I, P, P],
     "sc_debug_mag1c_clocks": [P],
+    "sc_debug_fastdiv": [ctypes.c_uint, ctypes.c_uint],
     "sc_ratio_workspace_bytes": [I, L],
     "sc_ratio_product": [P, P, P, I, L, F, F, P, P],
     "sc_weight_mag1c": [P, P, L, P],
@@ -77,7 +78,8 @@ SIGNATURES = {
 }
 _RESTYPES = {"sc_last_cuda_error": ctypes.c_char_p, "sc_mag1c_smem_bytes": c_int64, "sc_bn_partials_bytes": c_int64, "sc_mlr_workspace_bytes": c_int64, "sc_dwconv_wgrad_workspace_bytes": c_int64, "sc_head_wgrad_workspace_bytes": c_int64,
              "sc_ratio_workspace_bytes": c_int64, "sc_conv_wgrad_workspace_bytes": c_int64,
-             "sc_tc_conv_wgrad_workspace_bytes": c_int64, "sc_tc_wgrad_halo_workspace_bytes": c_int64, "sc_bce_loss_words": c_int64}
+             "sc_tc_conv_wgrad_workspace_bytes": c_int64, "sc_tc_wgrad_halo_workspace_bytes": c_int64, "sc_bce_loss_words": c_int64,
+             "sc_debug_fastdiv": ctypes.c_uint}
 
 _lib = None
 

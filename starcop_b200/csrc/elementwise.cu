@@ -21,6 +21,12 @@ bool pdl_enabled() {
 using namespace sc;
 
 extern "C" int sc_abi_version(void) { return 1; }
+// host-side check of the tile-index division constants (common.cuh, FastDiv): the same formula the kernels evaluate
+extern "C" unsigned int sc_debug_fastdiv(unsigned int x, unsigned int d) {
+  if (d == 0) return 0;
+  const FastDiv f = make_fastdiv(d);
+  return (unsigned int)(((((unsigned long long)f.m * x) >> 32) + x) >> f.s);
+}
 extern "C" const char* sc_last_cuda_error(void) { return cudaGetErrorString(sc::g_last_error); }
 
 // ------------------------------------------------------------------------------------------------

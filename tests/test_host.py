@@ -22,6 +22,21 @@ def test_library_exports_every_declared_symbol():
     assert lib.sc_abi_version() == 1
 
 
+def test_fastdiv_constants_are_exact():
+    """the multiply-high division the persistent tile loops use to decode (image, tile row, tile column): exact for
+    every divisor / dividend class the kernels can see (0 <= x < 2^31), evaluated by the library's own host code"""
+    import random
+    from starcop_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    rng = random.Random(0)
+    divisors = list(range(1, 70)) + [127, 128, 129, 255, 256, 257, 1000, 4095, 4096, 4097, 65535, 65536, 1 << 20, (1 << 24) + 3]
+    for d in divisors:
+        xs = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, (1 << 31) - 1, (1 << 31) - 2] + [rng.randrange(1 << 31) for _ in range(200)]
+        for x in xs:
+            assert lib.sc_debug_fastdiv(x, d) == x // d, (x, d)
+
+
 def test_product_does_not_import_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "starcop_b200")):
         for f in files:
