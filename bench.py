@@ -612,7 +612,8 @@ def main():
                                    f"{args.dtype} storage fp32 accumulate, BN train mode",
                        "global_batch": world * B, "tile": [S, S, 4], "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations > 2 GB) exceeds the 126 MB L2",
-                       "schedule": "one CUDA graph per step captured on a high-priority stream; weight gradients on "
+                       "schedule": "one CUDA graph per step captured on a " + ("default" if os.environ.get("STARCOP_MAIN_PRIO") == "0" else "high")
+                                   + "-priority stream; weight gradients on "
                                    + os.environ.get("STARCOP_SIDE_STREAMS", "2") + " default-priority side stream(s); "
                                    "programmatic dependent launch " + ("off" if os.environ.get("STARCOP_PDL") == "0" else "on")},
             "e2e": {"value": e2e_val, "unit": "tiles/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
